@@ -1,0 +1,534 @@
+// rip_fused.cu -- gray -> 5x5 Gaussian -> 3x3 Sobel in ONE kernel (one HBM round trip per frame),
+// and the same kernel without the blur stage (gray -> Sobel, BASELINE config 3).
+//
+// Design (sm_100a, HBM/issue-bound integer+fp32 stencil; no tensor cores by design):
+//   * every WARP is independent.  A lane owns 4 horizontally adjacent pixels; a warp covers 128
+//     pixels of which the middle 120 (lanes 1..30) are outputs and the outer lanes are halo.
+//     The warp slides DOWN a row segment, so the vertical halo costs 6 warm-up rows per segment
+//     and the horizontal halo 8/128 of the lanes.  No shared memory, no block barriers.
+//   * per new image row a lane loads its 12 (RGB) or 16 (RGBA) bytes with 32/128-bit loads that
+//     are prefetched two rows ahead, converts to the reference's exact gray, and keeps the last 5
+//     gray rows / 2 Sobel partial rows in REGISTERS (the loop is unrolled by 10 = lcm(5,2) so the
+//     ring indices are compile-time constants and no register moves are needed).
+//   * the horizontal neighbours (2 per side for the blur, 1 per side for Sobel) come from the
+//     adjacent lanes with warp shuffles.
+//   * exactness: the blurred value must equal the reference's sequential, unfused, 25-tap fp32
+//     sum truncated to u8 (GaussianBlur.cpp:236-258).  The fast path evaluates a separable fp32
+//     sum S~ and rounds with a magic-number add; a pixel whose S~ is closer to an integer than the
+//     proven bound on |S~ - S_ref| (rip_fused_band below) is recomputed with the exact 25-tap
+//     sequence (__fmul_rn/__fadd_rn in the reference order).  So the u8 blurred image, and with it
+//     the Sobel output, is bit-exact, at separable cost on all but ~0.1 % of the pixels.
+//   * Sobel: gx, gy from separable partial sums in fp32 (small integers, exact), magnitude via
+//     sqrt.approx (its error is 8x below the distance of any integer's root to a rounding
+//     boundary for results < 255.5), saturate, round with the magic-number add, pack 4 bytes,
+//     one 32-bit store per lane per row.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "rip_common.cuh"
+#include "rip_internal.h"
+
+namespace rip {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kBandPx = 120;      // output pixels per warp per row (lanes 1..30 x 4 px)
+constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: x + kMagic rounds x to the nearest integer (ties to even)
+
+struct FusedParams {
+    const uint8_t *in;
+    uint8_t *out;
+    int W, H;
+    int in_row0, in_rows, out_row0, out_rows;
+    int seg_rows, n_segs, n_bands, n_band_groups;
+    float g0, g1, g2;    // separable taps: w2d[ky][kx] ~= g[|ky|] * g[|kx|]
+    float thr;           // slow path if |frac - 0.5| > thr  (thr = 0.5 - band)
+    float w[25];         // exact 2-D weights for the slow path
+    unsigned long long *slow_counter;  // optional statistics (NULL in production)
+};
+
+// ---- exact gray of 4 packed pixels -> 4 floats ------------------------------------------------
+// t = 299r + 587g + 114b via two 2-way dot products per pixel; q = floor(t/1000) = hi32(t * 4294968)
+// (exact for t <= 255000: 4294968*1000 - 2^32 = 704 and 255000*704 < 2^32); t % 1000 == 0 iff the
+// low word of that product is < 2^18 (it is 704*q <= 179520 then, and >= 4294968 otherwise).
+// The 64-bit addend puts 0x4B000000 into the high word: the bits of the float 2^23 + q.
+__device__ __forceinline__ void gray_mul(uint32_t t, uint32_t &lo, float &f)
+{
+    unsigned long long prod;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(prod) : "r"(t), "r"(4294968u), "l"(0x4B00000000000000ull));
+    lo = (uint32_t)prod;
+    f = __uint_as_float((uint32_t)(prod >> 32)) - 8388608.0f;
+}
+
+// t is a multiple of 1000: replay the reference's double evaluation (Comparator.cpp:41)
+__device__ __forceinline__ float gray_slow(uint32_t r, uint32_t g, uint32_t b)
+{
+    const double s = __dadd_rn(__dadd_rn(__dmul_rn(0.299, (double)r), __dmul_rn(0.587, (double)g)),
+                               __dmul_rn(0.114, (double)b));
+    return (float)__double2int_rz(s);
+}
+
+template <int CN, bool BGR>
+__device__ __forceinline__ void gray4(const uint32_t *w, float f[4])
+{
+    constexpr uint32_t cA = BGR ? 114u : 299u, cB = 587u, cC = BGR ? 299u : 114u;  // weights of byte 0,1,2
+    constexpr uint32_t AB = cA | (cB << 16), C0 = cC, zA = cA << 16, BC = cB | (cC << 16);
+    uint32_t t[4], lo[4];
+    if constexpr (CN == 4) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) t[j] = __dp2a_hi(C0, w[j], __dp2a_lo(AB, w[j], 0u));  // alpha x 0
+    } else {
+        // byte stream: p0 = w0.b0-2, p1 = w0.b3 w1.b0-1, p2 = w1.b2-3 w2.b0, p3 = w2.b1-3
+        t[0] = __dp2a_hi(C0, w[0], __dp2a_lo(AB, w[0], 0u));
+        t[1] = __dp2a_lo(BC, w[1], __dp2a_hi(zA, w[0], 0u));
+        t[2] = __dp2a_lo(C0, w[2], __dp2a_hi(AB, w[1], 0u));
+        t[3] = __dp2a_hi(BC, w[2], __dp2a_lo(zA, w[2], 0u));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) gray_mul(t[j], lo[j], f[j]);
+    if (min(min(lo[0], lo[1]), min(lo[2], lo[3])) < (1u << 18)) {  // rare (always on r=g=b greys)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (lo[j] < (1u << 18)) {
+                uint32_t c0, c1, c2;
+                if constexpr (CN == 4) {
+                    c0 = w[j] & 0xffu; c1 = (w[j] >> 8) & 0xffu; c2 = (w[j] >> 16) & 0xffu;
+                } else {
+                    const unsigned long long s01 = ((unsigned long long)w[1] << 32) | w[0];
+                    const unsigned long long s12 = ((unsigned long long)w[2] << 32) | w[1];
+                    const uint32_t px = j == 0 ? w[0] : j == 1 ? (uint32_t)(s01 >> 24) : j == 2 ? (uint32_t)(s12 >> 16) : (w[2] >> 8);
+                    c0 = px & 0xffu; c1 = (px >> 8) & 0xffu; c2 = (px >> 16) & 0xffu;
+                }
+                f[j] = BGR ? gray_slow(c2, c1, c0) : gray_slow(c0, c1, c2);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int CN>
+struct RawRow {
+    uint32_t w[CN];  // CN 32-bit words = 4 pixels of CN bytes
+};
+
+template <int CN>
+__device__ __forceinline__ RawRow<CN> load_row(const uint8_t *p, bool valid)
+{
+    RawRow<CN> r;
+#pragma unroll
+    for (int i = 0; i < CN; i++) r.w[i] = 0;
+    if (valid) {
+        if constexpr (CN == 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+            r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+        } else {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+            r.w[0] = __ldg(q); r.w[1] = __ldg(q + 1); r.w[2] = __ldg(q + 2);
+        }
+    }
+    return r;
+}
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int PF = 5;      // rows prefetched ahead ...
+constexpr int UNROLL = 5;  // ... = ring period of the gray rows = unroll factor of the row loop
+
+// Per-warp sliding-window state; lives entirely in registers (all indices are compile-time, and
+// a ring slot only occupies registers while its value is live).
+template <int CN>
+struct WarpState {
+    float G[5][4];   // gray rows r-4..r                                   (slot = phase % 5)
+    float Dr[5][4];  // b[x+1]-b[x-1]       of blurred rows; only the last two are live
+    float Sr[5][4];  // b[x-1]+2b[x]+b[x+1] of blurred rows; only the last two are live
+    RawRow<CN> pre[PF];
+};
+
+struct Geometry {
+    const uint8_t *in_base;  // frame's input band   (warp-uniform)
+    uint8_t *out_base;       // frame's output band  (warp-uniform)
+    uint32_t in_pitch;
+    uint32_t soff;           // byte offset of this lane's pixels in the row that is prefetched next
+    int doff;                // byte offset of this lane's pixels in the output row produced next
+    int lane, lane_last;
+    bool edge, left_edge, right_edge, in_img, store_lane;
+    int ys;                  // first output row of the segment
+};
+
+// Sobel magnitude of one output row from the partial sums of blurred rows yo-1, yo, yo+1.
+__device__ __forceinline__ uint32_t sobel_pack(const float *D0, const float *D1, const float *D2, const float *S0,
+                                               const float *S2)
+{
+    float q[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float gx = fmaf(2.f, D1[j], D0[j] + D2[j]);
+        const float gy = S2[j] - S0[j];
+        const float m = sqrt_approx(fmaf(gx, gx, gy * gy));
+        q[j] = fminf(m, 255.f) + kMagic;  // saturate, round half to even: result in the low byte
+    }
+    const uint32_t q01 = __byte_perm(__float_as_uint(q[0]), __float_as_uint(q[1]), 0x0040);
+    const uint32_t q23 = __byte_perm(__float_as_uint(q[2]), __float_as_uint(q[3]), 0x0040);
+    return __byte_perm(q01, q23, 0x5410);
+}
+
+// One image row of the sliding window.  PH = (r - r_first) % 5 fixes every ring slot statically.
+template <int PH, int CN, bool BGR, bool BLUR>
+__device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Geometry &geo, int r)
+{
+    const int W = p.W, H = p.H, lane = geo.lane;
+    // ---- 1. gray of the new row r; prefetch row r+PF (row index clamped to the image) -----------
+    float f[4];
+    {
+        const RawRow<CN> raw = st.pre[PH % PF];
+        st.pre[PH % PF] = load_row<CN>(geo.in_base + geo.soff, geo.in_img);
+        // next prefetch is row clamp(r+PF+1) -- clamped to the rows the input band holds
+        if ((unsigned)(r + PF - p.in_row0) < (unsigned)(p.in_rows - 1)) geo.soff += geo.in_pitch;
+        gray4<CN, BGR>(raw.w, f);
+    }
+    float b[4];  // blurred row yb as exact u8 values held in floats; without the blur stage: the gray row
+    const int yb = BLUR ? r - 2 : r;
+    if constexpr (BLUR) {
+        // clamp-to-edge columns (GaussianBlur.cpp:240): x < 0 -> column 0, x >= W -> column W-1
+        if (geo.edge) {
+            const float first = __shfl_sync(FULL, f[0], 1);
+            const float last = __shfl_sync(FULL, f[3], min(geo.lane_last, 31));
+            if (geo.left_edge && lane == 0) f[0] = f[1] = f[2] = f[3] = first;
+            if (geo.right_edge && lane > geo.lane_last) f[0] = f[1] = f[2] = f[3] = last;
+        }
+        constexpr int a = PH % 5;
+#pragma unroll
+        for (int j = 0; j < 4; j++) st.G[a][j] = f[j];
+        // slots by age: 0 (row r) = a, 1 = a+4, 2 = a+3, 3 = a+2, 4 (row r-4) = a+1   (mod 5)
+        float V[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float e2 = st.G[a][j] + st.G[(a + 1) % 5][j];
+            const float e1 = st.G[(a + 4) % 5][j] + st.G[(a + 2) % 5][j];
+            V[j] = fmaf(p.g2, e2, fmaf(p.g1, e1, p.g0 * st.G[(a + 3) % 5][j]));
+        }
+        const float Vm2 = __shfl_up_sync(FULL, V[2], 1), Vm1 = __shfl_up_sync(FULL, V[3], 1);
+        const float Vp4 = __shfl_down_sync(FULL, V[0], 1), Vp5 = __shfl_down_sync(FULL, V[1], 1);
+        const float c[8] = {Vm2, Vm1, V[0], V[1], V[2], V[3], Vp4, Vp5};
+        float d[4];
+        bool slow = false;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float e2 = c[j] + c[j + 4], e1 = c[j + 1] + c[j + 3];
+            const float u = fmaf(p.g2, e2, fmaf(p.g1, e1, fmaf(p.g0, c[j + 2], -0.5f)));  // S~ - 0.5
+            const float rr = u + kMagic;  // nearest integer to S~ - 0.5: floor(S~) outside the guard band
+            b[j] = rr - kMagic;
+            d[j] = u - b[j];              // frac(S~) - 0.5
+            slow = slow || (fabsf(d[j]) > p.thr);
+        }
+        if (__any_sync(FULL, slow)) {
+            // exact replay (reference order) for the flagged pixels; rows ky = -2..2 are ages 4..0
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ky = 0; ky < 5; ky++) {
+                const float *g = st.G[(a + 1 + ky) % 5];
+                const float gm2 = __shfl_up_sync(FULL, g[2], 1), gm1 = __shfl_up_sync(FULL, g[3], 1);
+                const float gp4 = __shfl_down_sync(FULL, g[0], 1), gp5 = __shfl_down_sync(FULL, g[1], 1);
+                const float cc[8] = {gm2, gm1, g[0], g[1], g[2], g[3], gp4, gp5};
+                if (slow) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+#pragma unroll
+                        for (int kx = 0; kx < 5; kx++)
+                            acc[j] = __fadd_rn(acc[j], __fmul_rn(cc[j + kx], p.w[ky * 5 + kx]));
+                }
+            }
+            if (slow) {
+                unsigned n = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (fabsf(d[j]) > p.thr) { b[j] = truncf(fminf(fmaxf(acc[j], 0.f), 255.f)); n++; }
+                if (p.slow_counter) atomicAdd(p.slow_counter, (unsigned long long)n);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = f[j];
+    }
+
+    // ---- 3. Sobel partial sums of row yb, BORDER_REFLECT_101 in x --------------------------------
+    float bl = __shfl_up_sync(FULL, b[3], 1), br = __shfl_down_sync(FULL, b[0], 1);
+    if (geo.edge) {
+        if (geo.left_edge && lane == 1) bl = b[1];                 // x = -1 -> x = 1
+        if (geo.right_edge && lane == geo.lane_last) br = b[2];    // x = W  -> x = W-2
+    }
+    constexpr int s0 = (PH + 3) % 5, s1 = (PH + 4) % 5, s2 = PH % 5;  // slots of blurred rows yb-2, yb-1, yb
+    {
+        const float e[6] = {bl, b[0], b[1], b[2], b[3], br};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            st.Dr[s2][j] = e[j + 2] - e[j];
+            st.Sr[s2][j] = fmaf(2.f, e[j + 1], e[j] + e[j + 2]);
+        }
+    }
+    // ---- 4. output row yo = yb-1 from blurred rows yo-1, yo, yo+1 --------------------------------
+    const int yo = yb - 1;
+    if (yo >= geo.ys) {  // warp-uniform; false only during the warm-up rows of the segment
+        uint32_t packed;
+        if (yo == 0) {            // BORDER_REFLECT_101 in y: row -1 -> row 1
+            packed = sobel_pack(st.Dr[s2], st.Dr[s1], st.Dr[s2], st.Sr[s2], st.Sr[s2]);
+        } else if (yb == H) {     // row H -> row H-2 (this iteration's input row is a dummy)
+            packed = sobel_pack(st.Dr[s0], st.Dr[s1], st.Dr[s0], st.Sr[s0], st.Sr[s0]);
+        } else {
+            packed = sobel_pack(st.Dr[s0], st.Dr[s1], st.Dr[s2], st.Sr[s0], st.Sr[s2]);
+        }
+        if (geo.store_lane) *reinterpret_cast<uint32_t *>(geo.out_base + (uint32_t)geo.doff) = packed;
+    }
+    geo.doff += W;
+}
+
+template <int CN, bool BGR, bool BLUR>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+fused_kernel(const __grid_constant__ FusedParams p)
+{
+    constexpr int HALO = BLUR ? 3 : 1;  // input rows above/below an output row
+
+    Geometry geo;
+    geo.lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int bid = blockIdx.x;
+    const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
+    const int seg = bid % p.n_segs;
+    const int frame = bid / p.n_segs;
+    const int band = bg * kWarpsPerBlock + warp;
+    if (band >= p.n_bands) return;  // warp-uniform, and there are no block-level barriers
+
+    const int W = p.W;
+    const int xw0 = band * kBandPx;
+    const int x = xw0 - 4 + 4 * geo.lane;        // first of this lane's 4 pixels
+    geo.in_img = (x >= 0) && (x < W);            // W % 4 == 0: a lane is fully inside or fully outside
+    geo.lane_last = (W - xw0) >> 2;              // lane holding pixels W-4..W-1 (may be > 31)
+    geo.left_edge = (band == 0);
+    geo.right_edge = (geo.lane_last <= 31);
+    geo.edge = geo.left_edge || geo.right_edge;
+    geo.ys = p.out_row0 + seg * p.seg_rows;
+    const int ye = min(geo.ys + p.seg_rows, p.out_row0 + p.out_rows);
+    geo.in_pitch = (uint32_t)W * CN;
+    geo.in_base = p.in + (size_t)frame * p.in_rows * geo.in_pitch;
+    geo.out_base = p.out + (size_t)frame * p.out_rows * W;
+    geo.store_lane = (geo.lane >= 1) && (geo.lane <= 30) && geo.in_img;
+
+    WarpState<CN> st;
+#pragma unroll
+    for (int i = 0; i < 5; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) st.G[i][j] = st.Dr[i][j] = st.Sr[i][j] = 0.f;
+
+    const int r_first = geo.ys - HALO, r_last = ye - 1 + HALO;
+    const uint32_t xoff = geo.in_img ? (uint32_t)x * CN : 0u;
+    // Row indices are clamped to the rows the input band holds.  The host guarantees the band
+    // covers every row an output needs, and that it starts at row 0 / ends at row H-1 wherever the
+    // clamp-to-edge rule (GaussianBlur.cpp:241) is actually exercised; other clamped rows are
+    // read-ahead only and never consumed.
+#pragma unroll
+    for (int i = 0; i < PF; i++) {
+        const int rs = min(max(r_first + i - p.in_row0, 0), p.in_rows - 1);
+        st.pre[i] = load_row<CN>(geo.in_base + (uint32_t)rs * geo.in_pitch + xoff, geo.in_img);
+    }
+    geo.soff = (uint32_t)min(max(r_first + PF - p.in_row0, 0), p.in_rows - 1) * geo.in_pitch + xoff;
+    // output row produced by the step of input row r is r - HALO
+    geo.doff = (r_first - HALO - p.out_row0) * W + x;
+
+    int r = r_first;
+#define RIP_STEP(PH)                                   \
+    if (r > r_last) break;                             \
+    step<PH, CN, BGR, BLUR>(st, p, geo, r);            \
+    r++;
+    for (;;) {
+        RIP_STEP(0) RIP_STEP(1) RIP_STEP(2) RIP_STEP(3) RIP_STEP(4)
+    }
+#undef RIP_STEP
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+bool fused_supported(int W, int H, int fmt, int ksize, const uint8_t *d_in, const uint8_t *d_out)
+{
+    if (ksize != 0 && ksize != 5) return false;
+    if (W < 4 || (W & 3) || H < 2) return false;
+    const int cn = (fmt == RIP_FMT_RGB8 || fmt == RIP_FMT_BGR8) ? 3 : (fmt == RIP_FMT_RGBA8 || fmt == RIP_FMT_BGRA8) ? 4 : 0;
+    if (cn == 0) return false;
+    const uintptr_t in_align = cn == 4 ? 15u : 3u;
+    if ((reinterpret_cast<uintptr_t>(d_in) & in_align) || (reinterpret_cast<uintptr_t>(d_out) & 3u)) return false;
+    if (getenv("RIP_DISABLE_FUSED")) return false;
+    return true;
+}
+
+// Guard band for the fast path, and the separable taps that minimise it.  See DESIGN.md
+// ("Exact blur at separable cost") for the derivation:
+//   |S_ref - S| <= 25 u S (24 rounded adds + 25 rounded products, all terms >= 0, u = 2^-24)
+//   |S~    - S| <= 255 * sum|w_ij - g_i g_j|  +  10 u S (separable evaluation with FMAs)
+// with S <= 255 * sum(w).  The kernel compares |frac(S~) - 0.5| against 0.5 - band.
+bool fused_plan_weights(const float *w25, float g[3], float *thr)
+{
+    double sum = 0.0;
+    for (int i = 0; i < 25; i++) {
+        if (!(w25[i] >= 0.0f) || !std::isfinite(w25[i])) return false;
+        sum += (double)w25[i];
+    }
+    if (!(sum > 0.0) || 255.0 * sum >= 255.9) return false;  // floor(S) must stay <= 255
+    // symmetric separable fit from the diagonal: g_k = sqrt(w[k][k])
+    double gd[3];
+    for (int k = 0; k < 3; k++) gd[k] = std::sqrt((double)w25[(2 + k) * 5 + (2 + k)]);
+    for (int k = 0; k < 3; k++) g[k] = (float)gd[k];
+    double dev = 0.0;
+    for (int ky = -2; ky <= 2; ky++)
+        for (int kx = -2; kx <= 2; kx++)
+            dev += std::fabs((double)w25[(ky + 2) * 5 + (kx + 2)] - (double)g[std::abs(ky)] * (double)g[std::abs(kx)]);
+    const double u = std::ldexp(1.0, -24);
+    const double smax = 255.0 * sum;
+    const double band = 255.0 * dev + (25.0 + 10.0 + 3.0) * u * smax * 1.01 + 1e-6;
+    if (band > 0.05) return false;  // weights are not (close to) a symmetric separable kernel
+    *thr = (float)(0.5 - band);
+    return true;
+}
+
+static int pick_seg_rows(int out_rows, int n_frames, int n_band_groups, int device)
+{
+    if (const char *e = getenv("RIP_FUSED_SEG")) {
+        const int v = atoi(e);
+        if (v > 0) return v < out_rows ? v : out_rows;
+    }
+    // enough blocks for >= ~8 waves of (SMs x 6 resident blocks), but segments of >= 64 rows so the
+    // 6 warm-up rows stay below 10 %; never more than 256 rows (tail balance).
+    const long long target_blocks = (long long)sm_count(device) * 6 * 8;
+    int seg = 256;
+    while (seg > 64 && (long long)n_frames * n_band_groups * ((out_rows + seg - 1) / seg) < target_blocks) seg >>= 1;
+    if (seg > out_rows) seg = out_rows;
+    return seg;
+}
+
+static unsigned long long *g_slow_counter = nullptr;  // set by rip_debug_set_slow_counter
+
+template <int CN, bool BGR>
+static void launch_t(bool blur, dim3 grid, cudaStream_t s, const FusedParams &p)
+{
+    if (blur) fused_kernel<CN, BGR, true><<<grid, kWarpsPerBlock * 32, 0, s>>>(p);
+    else fused_kernel<CN, BGR, false><<<grid, kWarpsPerBlock * 32, 0, s>>>(p);
+}
+
+int launch_fused(cudaStream_t s, const uint8_t *d_in, uint8_t *d_out, int W, int H, int n_frames, int fmt,
+                 bool with_blur, const float *weights25, int in_row0, int in_rows, int out_row0, int out_rows,
+                 int device)
+{
+    FusedParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = d_in; p.out = d_out; p.W = W; p.H = H;
+    p.in_row0 = in_row0; p.in_rows = in_rows; p.out_row0 = out_row0; p.out_rows = out_rows;
+    p.n_bands = (W + kBandPx - 1) / kBandPx;
+    p.n_band_groups = (p.n_bands + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    p.seg_rows = pick_seg_rows(out_rows, n_frames, p.n_band_groups, device);
+    p.n_segs = (out_rows + p.seg_rows - 1) / p.seg_rows;
+    p.slow_counter = g_slow_counter;
+    if (with_blur) {
+        float g[3];
+        if (!fused_plan_weights(weights25, g, &p.thr))
+            return fail(RIP_EUNSUPPORTED, "rip_fused: weights are not a non-negative symmetric separable 5x5 kernel");
+        p.g0 = g[0]; p.g1 = g[1]; p.g2 = g[2];
+        memcpy(p.w, weights25, sizeof(float) * 25);
+    }
+    const long long blocks = (long long)n_frames * p.n_segs * p.n_band_groups;
+    if (blocks <= 0 || blocks > 0x7fffffffLL) return fail(RIP_EINVAL, "rip_fused: grid of %lld blocks is out of range", blocks);
+    const dim3 grid((unsigned)blocks);
+    switch (fmt) {
+    case RIP_FMT_RGB8:  launch_t<3, false>(with_blur, grid, s, p); break;
+    case RIP_FMT_BGR8:  launch_t<3, true>(with_blur, grid, s, p); break;
+    case RIP_FMT_RGBA8: launch_t<4, false>(with_blur, grid, s, p); break;
+    case RIP_FMT_BGRA8: launch_t<4, true>(with_blur, grid, s, p); break;
+    default: return fail(RIP_EINVAL, "rip_fused: unsupported input format %d", fmt);
+    }
+    RIP_LAUNCH_CHECK();
+    return RIP_OK;
+}
+
+void fused_set_slow_counter(unsigned long long *d_counter) { g_slow_counter = d_counter; }
+
+// ---------------------------------------------------------------------------------------------
+// device self-test of the two arithmetic shortcuts the fused kernel relies on, exhaustively:
+//   (1) min(255, rint(sqrt.approx(m2))) == min(255, rint(sqrt_rn(m2))) for every reachable
+//       m2 = gx^2 + gy^2 <= 2 * 1020^2;
+//   (2) the dp2a / mad.wide gray path == gray_exact() for all 2^24 (c0,c1,c2) triples, for the RGB
+//       and RGBA packers in both channel orders.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void selftest_sqrt_kernel(unsigned long long *bad)
+{
+    const unsigned m2_max = 2u * 1020u * 1020u;
+    for (unsigned m2 = blockIdx.x * blockDim.x + threadIdx.x; m2 <= m2_max; m2 += gridDim.x * blockDim.x) {
+        const float q = fminf(sqrt_approx((float)m2), 255.f) + kMagic;
+        const unsigned got = __float_as_uint(q) & 0xffu;
+        const unsigned want = (unsigned)min(__float2int_rn(__fsqrt_rn((float)m2)), 255);
+        if (got != want) atomicAdd(bad, 1ull);
+    }
+}
+
+template <int CN, bool BGR>
+__global__ void selftest_gray_kernel(unsigned long long *bad)
+{
+    // thread q handles triples 4q..4q+3 (triple index i: c0 = i & 255, c1 = (i >> 8) & 255, c2 = i >> 16)
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < (1u << 22); q += gridDim.x * blockDim.x) {
+        uint8_t bytes[16];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned i = 4 * q + j;
+            bytes[CN * j + 0] = i & 255u; bytes[CN * j + 1] = (i >> 8) & 255u; bytes[CN * j + 2] = i >> 16;
+            if (CN == 4) bytes[4 * j + 3] = (uint8_t)(i * 37u);  // alpha must be ignored
+        }
+        uint32_t w[CN];
+#pragma unroll
+        for (int k = 0; k < CN; k++)
+            w[k] = bytes[4 * k] | (bytes[4 * k + 1] << 8) | (bytes[4 * k + 2] << 16) | ((uint32_t)bytes[4 * k + 3] << 24);
+        float f[4];
+        gray4<CN, BGR>(w, f);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned i = 4 * q + j;
+            const unsigned c0 = i & 255u, c1 = (i >> 8) & 255u, c2 = i >> 16;
+            const unsigned want = BGR ? gray_exact(c2, c1, c0) : gray_exact(c0, c1, c2);
+            if (f[j] != (float)want) atomicAdd(bad, 1ull);
+        }
+    }
+}
+
+}  // namespace
+
+int fused_selftest(int device, unsigned long long *checked, unsigned long long *mismatches)
+{
+    unsigned long long *d_bad = nullptr;
+    RIP_CUDA(cudaMalloc(&d_bad, sizeof(*d_bad)));
+    RIP_CUDA(cudaMemset(d_bad, 0, sizeof(*d_bad)));
+    const int grid = sm_count(device) * 8;
+    selftest_sqrt_kernel<<<grid, 256>>>(d_bad);
+    selftest_gray_kernel<3, false><<<grid, 256>>>(d_bad);
+    selftest_gray_kernel<3, true><<<grid, 256>>>(d_bad);
+    selftest_gray_kernel<4, false><<<grid, 256>>>(d_bad);
+    selftest_gray_kernel<4, true><<<grid, 256>>>(d_bad);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    unsigned long long bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) return cuda_fail(e, "fused_selftest", __FILE__, __LINE__);
+    count_launch(5);
+    *checked = (2ull * 1020ull * 1020ull + 1ull) + 4ull * (1ull << 24);
+    *mismatches = bad;
+    return RIP_OK;
+}
+
+}  // namespace rip

@@ -1,0 +1,321 @@
+"""GPU parity: every CUDA path against the CPU oracle, bit-exact, through the C ABI.
+
+Run on a B200 with `pytest -m gpu`.  Sizes are chosen so the oracle finishes in seconds; the
+BASELINE-size cases use all host threads for the oracle and size-independent properties
+(frame independence, band/whole-frame equality)."""
+import numpy as np
+import pytest
+
+import rip_b200 as rip
+from conftest import bgr_to_rgba, synth_frame
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    if rip.device_count() < 1:
+        pytest.fail("GPU tests need a CUDA device: librip_cuda has no CPU fallback")
+    c = rip.Context([0])
+    yield c
+    c.close()
+
+
+def _eq(got, want, what=""):
+    if not np.array_equal(got, want):
+        d = np.abs(got.astype(int) - want.astype(int))
+        idx = np.argwhere(d > 0)
+        raise AssertionError(f"{what}: {len(idx)} of {d.size} bytes differ, max abs {d.max()}, first at {idx[0].tolist()}")
+
+
+# ---------------------------------------------------------------------------------------------
+def test_native_library_loaded_and_counts_launches(ctx):
+    before = rip.launch_count()
+    ctx.process(np.zeros((8, 8, 3), np.uint8), rip.OP_GRAY, rip.FMT_RGB8)
+    assert rip.launch_count() > before
+    info = rip.device_info(0)
+    assert info.cc_major == 10, f"expected a Blackwell sm_100 device, got cc {info.cc_major}.{info.cc_minor}"
+
+
+def test_device_selftest_of_arithmetic_shortcuts():
+    checked, bad = rip.selftest(0)
+    assert checked > 4 * (1 << 24) and bad == 0, (checked, bad)
+
+
+# ---- gray (config 1) -------------------------------------------------------------------------
+def test_gray_all_16777216_triples(ctx, oracle):
+    i = np.arange(1 << 24, dtype=np.uint32)
+    rgb = np.stack([i & 255, (i >> 8) & 255, i >> 16], -1).astype(np.uint8).reshape(4096, 4096, 3)
+    _eq(ctx.process(rgb, rip.OP_GRAY, rip.FMT_RGB8), oracle.gray(rgb, threads=0), "gray RGB exhaustive")
+
+
+def test_gray_config1_tulips_medium640(ctx, oracle, golden_images):
+    bgr = golden_images["Tulips_medium640.bgr"]
+    rgba = bgr_to_rgba(bgr)
+    want = oracle.gray(bgr, oracle.BGR)
+    # drop-in container of Controller::PerformCLImageGrayscaling: (g,g,g,255) W*H*4
+    got = ctx.process(rgba, rip.OP_GRAY, rip.FMT_RGBA8, gray_out=rip.GRAY_OUT_RGBA)
+    assert got.shape == (512, 640, 4)
+    for c in range(3):
+        _eq(got[..., c], want, "gray RGBA->RGBA")
+    assert (got[..., 3] == 255).all()
+    _eq(ctx.process(rgba, rip.OP_GRAY, rip.FMT_RGBA8), want, "gray RGBA->u8")
+    _eq(ctx.process(np.ascontiguousarray(bgr), rip.OP_GRAY, rip.FMT_BGR8), want, "gray BGR->u8")
+
+
+@pytest.mark.parametrize("fmt,cn,order", [(rip.FMT_RGB8, 3, "RGB"), (rip.FMT_BGR8, 3, "BGR"),
+                                          (rip.FMT_RGBA8, 4, "RGB"), (rip.FMT_BGRA8, 4, "BGR")])
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (7, 9), (75, 75), (33, 130)])
+def test_gray_formats_and_ragged_sizes(ctx, oracle, fmt, cn, order, shape):
+    img = synth_frame("uniform", shape[0], shape[1], 11, cn)
+    img[0, 0, :3] = 1  # r=g=b=1 -> 0: the double-rounding case
+    want = oracle.gray(img, oracle.BGR if order == "BGR" else oracle.RGB)
+    _eq(ctx.process(img, rip.OP_GRAY, fmt), want, f"gray {order}{cn} {shape}")
+    got4 = ctx.process(img, rip.OP_GRAY, fmt, gray_out=rip.GRAY_OUT_RGBA)
+    _eq(got4[..., 1], want, "gray rgba container")
+
+
+def test_gray_grey_images_take_the_double_path(ctx, oracle):
+    v = np.arange(256, dtype=np.uint8)
+    img = np.repeat(np.tile(v, 4)[None, :, None], 3, axis=2).repeat(8, axis=0).copy()  # r=g=b
+    want = oracle.gray(img)
+    assert (want != img[..., 0]).sum() > 0  # 65 of the 256 greys come out v-1
+    _eq(ctx.process(img, rip.OP_GRAY, rip.FMT_RGB8), want, "grey ramp")
+
+
+# ---- Gaussian blur (config 2) ----------------------------------------------------------------
+@pytest.mark.parametrize("sigma", [1.0, 1.5])
+def test_blur_config2_artemis_large1024(ctx, oracle, golden_images, sigma):
+    rgba = bgr_to_rgba(golden_images["Artemis_large1024.bgr"])
+    assert rgba.shape == (1023, 683, 4)
+    w = rip.gauss_weights(5, sigma)
+    got = ctx.process(rgba, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=5, weights=w)
+    want = oracle.blur(rgba, 5, weights=oracle.gauss_weights(5, sigma), threads=0)
+    _eq(got, want, f"blur RGBA 5x5 sigma {sigma}")  # bit-exact, i.e. max/mean abs error 0
+
+
+@pytest.mark.parametrize("k,sigma", [(1, 1.0), (3, 0.8), (7, 2.0), (17, 6.0), (31, 9.5)])
+def test_blur_generic_kernel_sizes(ctx, oracle, k, sigma):
+    img = synth_frame("smooth", 61, 83, 5, 4)
+    w = rip.gauss_weights(k, sigma)
+    _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), oracle.blur(img, k, weights=w, threads=0),
+        f"blur K={k}")
+    g = np.ascontiguousarray(img[..., 0])
+    _eq(ctx.process(g, rip.OP_GAUSSIAN, rip.FMT_GRAY8, ksize=k, weights=w), oracle.blur(g, k, weights=w, threads=0),
+        f"blur gray K={k}")
+
+
+def test_blur_flat_regions_sigma15_lose_one_level(ctx, oracle):
+    flat = np.full((20, 24, 4), 255, np.uint8)
+    got = ctx.process(flat, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=5, weights=rip.gauss_weights(5, 1.5))
+    assert (got == 254).all()  # what the reference CPU path does (sum of float weights < 1)
+    got = ctx.process(flat, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=5, weights=rip.gauss_weights(5, 1.0))
+    assert (got == 255).all()
+
+
+def test_blur_rejects_bad_arguments(ctx):
+    img = np.zeros((8, 8, 4), np.uint8)
+    with pytest.raises(rip.RipError):
+        ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=4, weights=np.ones((4, 4), np.float32))
+    with pytest.raises(rip.RipError):
+        ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=5, weights=None)
+
+
+# ---- Sobel (config 3) ------------------------------------------------------------------------
+def test_sobel_gray_input_matches_opencv_goldens(ctx, golden_cv2_sobel, golden_images):
+    for k, v in golden_cv2_sobel.items():
+        if k.startswith("syn.") and k.endswith(".in"):
+            if min(v.shape) < 2:
+                continue
+            _eq(ctx.process(v, rip.OP_EDGE, rip.FMT_GRAY8), golden_cv2_sobel[k[:-3] + ".out"], k)
+        elif not k.startswith("syn."):
+            _eq(ctx.process(golden_images[k + ".imread_gray"], rip.OP_EDGE, rip.FMT_GRAY8), v, k)
+
+
+@pytest.mark.parametrize("shape", [(2, 4), (2, 8), (5, 12), (37, 120), (37, 124), (64, 128), (33, 244), (75, 75), (19, 241)])
+@pytest.mark.parametrize("fmt,cn", [(rip.FMT_RGB8, 3), (rip.FMT_RGBA8, 4), (rip.FMT_BGR8, 3)])
+def test_sobel_colour_input(ctx, oracle, shape, fmt, cn):
+    img = synth_frame("uniform", shape[0], shape[1], 21, cn)
+    g = oracle.gray(img, oracle.BGR if fmt == rip.FMT_BGR8 else oracle.RGB)
+    _eq(ctx.process(img, rip.OP_EDGE, fmt), oracle.sobel(g), f"sobel colour {shape} cn={cn}")
+
+
+def test_sobel_config3_1080p_batch(ctx, oracle):
+    n = 8  # batch 64 in the bench; 8 distinct frames here, frame independence checked below
+    frames = np.stack([synth_frame("uniform", 1080, 1920, 0xB200 + 3000 + i) for i in range(n)])
+    got = ctx.process(frames, rip.OP_EDGE, rip.FMT_RGB8)
+    for i in range(n):
+        _eq(got[i], oracle.sobel(oracle.gray(frames[i], threads=0), threads=0), f"sobel 1080p frame {i}")
+    rep = np.concatenate([frames[:2]] * 8)  # 16 frames, only 2 distinct
+    out = ctx.process(rep, rip.OP_EDGE, rip.FMT_RGB8)
+    for i in range(16):
+        _eq(out[i], got[i % 2], "frame independence")
+
+
+# ---- fused gray -> blur -> Sobel (configs 4, 5) ------------------------------------------------
+FUSED_SHAPES = [(2, 4), (3, 8), (7, 12), (16, 120), (40, 124), (9, 128), (70, 244), (130, 364), (300, 480), (64, 1920)]
+
+
+@pytest.mark.parametrize("shape", FUSED_SHAPES)
+@pytest.mark.parametrize("kind", ["uniform", "smooth"])
+def test_fused_single_kernel_path(ctx, oracle, shape, kind):
+    img = synth_frame(kind, shape[0], shape[1], 31)
+    w = rip.gauss_weights(5, 1.0)
+    _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w, threads=0),
+        f"fused {kind} {shape}")
+
+
+@pytest.mark.parametrize("fmt,cn,order", [(rip.FMT_RGBA8, 4, "RGB"), (rip.FMT_BGR8, 3, "BGR"), (rip.FMT_BGRA8, 4, "BGR")])
+@pytest.mark.parametrize("sigma", [1.0, 1.5])
+def test_fused_formats_and_sigmas(ctx, oracle, fmt, cn, order, sigma):
+    img = synth_frame("smooth", 97, 248, 41, cn)
+    w = rip.gauss_weights(5, sigma)
+    want = oracle.fused(img, 5, weights=w, order=oracle.BGR if order == "BGR" else oracle.RGB)
+    _eq(ctx.process(img, rip.OP_FUSED, fmt, ksize=5, weights=w), want, f"fused {order}{cn} sigma {sigma}")
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (5, 5), (75, 75), (33, 241), (40, 683)])
+def test_fused_staged_path_for_odd_shapes(ctx, oracle, shape):
+    img = synth_frame("uniform", shape[0], shape[1], 51)
+    w = rip.gauss_weights(5, 1.0)
+    _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w), f"fused staged {shape}")
+
+
+@pytest.mark.parametrize("k,sigma", [(3, 0.8), (7, 2.0), (17, 6.0)])
+def test_fused_other_kernel_sizes(ctx, oracle, k, sigma):
+    img = synth_frame("smooth", 90, 160, 61)
+    w = rip.gauss_weights(k, sigma)
+    _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=k, weights=w), oracle.fused(img, k, weights=w, threads=0), f"fused K={k}")
+
+
+def _adversarial(h, w):
+    yy, xx = np.mgrid[0:h, 0:w]
+    frames = {"zeros": np.zeros((h, w), np.uint8), "ones255": np.full((h, w), 255, np.uint8)}
+    for v in (1, 2, 4, 127, 254):
+        frames[f"flat{v}"] = np.full((h, w), v, np.uint8)
+    frames["hramp"] = (xx % 256).astype(np.uint8)
+    frames["vramp"] = (yy % 256).astype(np.uint8)
+    frames["checker"] = (((xx + yy) & 1) * 255).astype(np.uint8)
+    c = np.zeros((h, w), np.uint8)
+    c[0, 0] = c[0, -1] = c[-1, 0] = c[-1, -1] = c[h // 2, 0] = c[0, w // 2] = 255
+    frames["corners"] = c
+    return {k: np.repeat(v[..., None], 3, axis=2).copy() for k, v in frames.items()}
+
+
+@pytest.mark.parametrize("sigma", [1.0, 1.5])
+def test_fused_adversarial_frames(ctx, oracle, sigma):
+    w = rip.gauss_weights(5, sigma)
+    for name, img in _adversarial(67, 252).items():
+        _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w), f"fused {name}")
+    # colour ramps exercise gray values off the grey diagonal
+    yy, xx = np.mgrid[0:67, 0:252]
+    img = np.stack([(xx * 3) % 256, (yy * 5 + xx) % 256, (xx + 2 * yy) % 256], -1).astype(np.uint8)
+    _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w), "fused colour ramps")
+
+
+def test_fused_guard_band_statistics():
+    """The exact replay must actually trigger (flat frames: always) yet stay rare on noise."""
+    w = rip.gauss_weights(5, 1.0)
+    h, wd = 256, 480
+    d_out = rip.DeviceBuffer(h * wd)
+    for kind, lo, hi in (("uniform", 1e-5, 5e-3), ("flat", 0.5, 1.5)):
+        img = synth_frame("uniform", h, wd, 71) if kind == "uniform" else np.full((h, wd, 3), 77, np.uint8)
+        d_in = rip.DeviceBuffer(img.nbytes).upload(img)
+        rip.slow_path_stats(True)
+        rip.fused_dev(d_in.ptr, d_out.ptr, wd, h, 1, rip.FMT_RGB8, 5, w)
+        frac = rip.slow_path_stats(False) / (h * wd)
+        assert lo <= frac <= hi, (kind, frac)
+
+
+def test_fused_row_bands_equal_whole_frame(ctx, oracle):
+    h, wd = 200, 360
+    img = synth_frame("uniform", h, wd, 81)
+    w = rip.gauss_weights(5, 1.0)
+    whole = oracle.fused(img, 5, weights=w, threads=0)
+    d_out = rip.DeviceBuffer(h * wd)
+    for nb in (2, 3, 8):
+        out = np.empty((h, wd), np.uint8)
+        for i in range(nb):
+            o0, o1 = h * i // nb, h * (i + 1) // nb
+            i0, i1 = max(0, o0 - 3), min(h, o1 + 3)
+            d_in = rip.DeviceBuffer((i1 - i0) * wd * 3).upload(img[i0:i1])
+            rip.fused_dev(d_in.ptr, d_out.ptr, wd, h, 1, rip.FMT_RGB8, 5, w, in_row0=i0, in_rows=i1 - i0, out_row0=o0, out_rows=o1 - o0)
+            out[o0:o1] = d_out.download((o1 - o0, wd))
+        _eq(out, whole, f"{nb} row bands")
+    # a band that does not cover its halo must be rejected, not silently clamped
+    d_in = rip.DeviceBuffer(50 * wd * 3)
+    with pytest.raises(rip.RipError, match="does not cover"):
+        rip.fused_dev(d_in.ptr, d_out.ptr, wd, h, 1, rip.FMT_RGB8, 5, w, in_row0=50, in_rows=50, out_row0=50, out_rows=50)
+    # banded host pipeline (one band per device of the context; 1 device -> 1 band)
+    _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w, banded=True), whole, "process_host_banded")
+
+
+def test_fused_config4_4k_frames(ctx, oracle):
+    w = rip.gauss_weights(5, 1.0)
+    distinct = [synth_frame("uniform", 2160, 3840, 0xB200 + 4000), synth_frame("smooth", 2160, 3840, 0xB200 + 4001)]
+    want = [oracle.fused(f, 5, weights=w, threads=0) for f in distinct]
+    frames = np.stack([distinct[i % 2] for i in range(6)])
+    got = ctx.process(frames, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w)
+    for i in range(6):
+        _eq(got[i], want[i % 2], f"fused 4K frame {i}")
+
+
+def test_fused_config5_8k_row_bands(oracle):
+    """8K frame as 8 row bands with 3-row halos through the device API (what 8 GPUs would each run)."""
+    h, wd = 4320, 7680
+    img = synth_frame("uniform", h, wd, 0xB200 + 5000)
+    w = rip.gauss_weights(5, 1.0)
+    want = oracle.fused(img, 5, weights=w, threads=0)
+    out = np.empty((h, wd), np.uint8)
+    nb = 8
+    d_out = rip.DeviceBuffer((h // nb + 1) * wd)
+    for i in range(nb):
+        o0, o1 = h * i // nb, h * (i + 1) // nb
+        i0, i1 = max(0, o0 - 3), min(h, o1 + 3)
+        d_in = rip.DeviceBuffer((i1 - i0) * wd * 3).upload(img[i0:i1])
+        rip.fused_dev(d_in.ptr, d_out.ptr, wd, h, 1, rip.FMT_RGB8, 5, w, in_row0=i0, in_rows=i1 - i0, out_row0=o0, out_rows=o1 - o0)
+        out[o0:o1] = d_out.download((o1 - o0, wd))
+        d_in.free()
+    _eq(out, want, "8K in 8 bands")
+
+
+def test_fused_non_separable_weights_fall_back_to_exact(ctx, oracle):
+    rng = np.random.default_rng(5)
+    w = rng.random((5, 5)).astype(np.float32)
+    w /= w.sum() * 1.001
+    img = synth_frame("uniform", 50, 120, 91)
+    _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w), "fused arbitrary weights")
+
+
+# ---- host pipeline plumbing --------------------------------------------------------------------
+def test_process_host_pinned_chunked_and_profiled(ctx, oracle):
+    n, h, wd = 40, 540, 960  # 62 MB of input: more than one 48 MiB chunk
+    pin = rip.PinnedBuffer(n * h * wd * 3)
+    frames = pin.array.reshape(n, h, wd, 3)
+    base = synth_frame("uniform", h, wd, 101)
+    for i in range(n):
+        frames[i] = np.roll(base, i, axis=1)
+    w = rip.gauss_weights(5, 1.0)
+    got, prof = ctx.process(frames, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w, prof=True)
+    for i in (0, 1, 17, 39):
+        _eq(got[i], oracle.fused(np.ascontiguousarray(frames[i]), 5, weights=w, threads=0), f"chunked frame {i}")
+    assert prof[0] == 0 and prof[1] <= prof[3] <= prof[5] and prof[5] > 0 and prof[2] == prof[1] and prof[4] == prof[3]
+    pin.free()
+
+
+def test_context_handles_mirror_the_opencl_objects(ctx):
+    import ctypes as C
+    L = rip.lib()
+    mod, ker, op = C.c_void_p(), C.c_void_p(), C.c_int(-1)
+    for variant, name, want in (("grayscale_base.cl", "grayscale", rip.OP_GRAY), ("gaussian_base.cl", "gaussian_blur", rip.OP_GAUSSIAN),
+                                ("edge_base.cl", "sobel_edge_detection", rip.OP_EDGE), ("fused", "fused", rip.OP_FUSED)):
+        rip.check(L.rip_module_load(ctx.ptr, variant.encode(), C.byref(mod)))
+        rip.check(L.rip_kernel_get(mod, name.encode(), C.byref(ker)))
+        rip.check(L.rip_kernel_op(ker, C.byref(op)))
+        assert op.value == want
+        L.rip_kernel_release(ker)
+        L.rip_module_release(mod)
+    rip.check(L.rip_module_load(ctx.ptr, b"grayscale_base.cl", C.byref(mod)))
+    assert L.rip_kernel_get(mod, b"gaussian_blur", C.byref(ker)) != 0  # wrong entry point for the module
+    assert L.rip_module_load(ctx.ptr, b"nonsense.cl", C.byref(ker)) != 0
+    L.rip_module_release(mod)
