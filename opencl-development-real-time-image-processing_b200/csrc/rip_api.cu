@@ -581,8 +581,11 @@ extern "C" int rip_fused(int device, rip_stream stream, const uint8_t *d_in, uin
                     in_row0, in_row0 + in_rows, g0, g1, out_row0, out_row0 + out_rows);
     DeviceGuard g(device);
     cudaStream_t s = (cudaStream_t)stream;
-    if (ksize == 5 && fused_supported(width, height, in_format, 5, d_in, d_out))
-        return launch_fused(s, d_in, d_out, width, height, n_frames, in_format, true, wts.w, in_row0, in_rows, out_row0, out_rows, device);
+    {
+        float g3[3], thr;  // single-kernel path: 5x5, aligned shape, and weights the guard band can cover
+        if (ksize == 5 && fused_supported(width, height, in_format, 5, d_in, d_out) && fused_plan_weights(wts.w, g3, &thr))
+            return launch_fused(s, d_in, d_out, width, height, n_frames, in_format, true, wts.w, in_row0, in_rows, out_row0, out_rows, device);
+    }
 
     // staged path: gray band -> exact KxK blur -> Sobel, through the caller's workspace
     size_t need = 0;
@@ -653,6 +656,13 @@ extern "C" int rip_out_bytes_per_frame(const rip_op_desc *desc, int width, int h
 }
 
 namespace {
+
+bool fused_single_kernel(int W, int H, int fmt, int ksize, const float *weights, const void *d_in, const void *d_out)
+{
+    float g3[3], thr;
+    return ksize == 5 && weights && fused_supported(W, H, fmt, 5, (const uint8_t *)d_in, (const uint8_t *)d_out) &&
+           fused_plan_weights(weights, g3, &thr);
+}
 
 struct Job {
     const rip_op_desc *desc;
@@ -732,7 +742,7 @@ int run_device(DevState &dev, const Job &job, const uint8_t *h_in, uint8_t *h_ou
             if ((rc = ensure(&b.d_in, &b.in_cap, job.in_frame_bytes * cf))) break;
             if ((rc = ensure(&b.d_out, &b.out_cap, job.out_frame_bytes * cf))) break;
             if (job.desc->op == RIP_OP_FUSED &&
-                !(job.desc->ksize == 5 && fused_supported(job.W, job.H, job.desc->in_format, 5, (const uint8_t *)b.d_in, (const uint8_t *)b.d_out))) {
+                !fused_single_kernel(job.W, job.H, job.desc->in_format, job.desc->ksize, job.desc->weights, b.d_in, b.d_out)) {
                 size_t ws_need = 0;  // staged path only
                 rip_fused_workspace_bytes(job.W, job.H, cf, job.desc->ksize, &ws_need);
                 if ((rc = ensure(&b.d_ws, &b.ws_cap, ws_need))) break;
@@ -855,7 +865,7 @@ extern "C" int rip_process_host_banded(rip_ctx *ctx, const rip_op_desc *desc, co
                     if ((rc = ensure(&b.d_in, &b.in_cap, row_in * (i1 - i0)))) break;
                     if ((rc = ensure(&b.d_out, &b.out_cap, (size_t)width * (o1 - o0)))) break;
                     if (desc->op == RIP_OP_FUSED &&
-                        !(desc->ksize == 5 && fused_supported(width, height, desc->in_format, 5, (const uint8_t *)b.d_in, (const uint8_t *)b.d_out))) {
+                        !fused_single_kernel(width, height, desc->in_format, desc->ksize, desc->weights, b.d_in, b.d_out)) {
                         size_t ws_need = 0;  // staged path only
                         rip_fused_workspace_bytes(width, i1 - i0, 1, desc->ksize, &ws_need);
                         if ((rc = ensure(&b.d_ws, &b.ws_cap, ws_need))) break;

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Minimal driver for profiling: N launches of one device-resident op, nothing else.
+
+    python tools/prof_fused.py [--op fused|sobel|gray] [--frames 8] [--w 3840 --h 2160] [--launches 4]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rip_b200 as rip  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--op", default="fused")
+ap.add_argument("--frames", type=int, default=8)
+ap.add_argument("--w", type=int, default=3840)
+ap.add_argument("--h", type=int, default=2160)
+ap.add_argument("--launches", type=int, default=4)
+ap.add_argument("--kind", default="uniform")
+a = ap.parse_args()
+
+rng = np.random.default_rng(1)
+if a.kind == "uniform":
+    one = rng.integers(0, 256, (a.h, a.w, 3), dtype=np.uint8)
+else:
+    one = np.full((a.h, a.w, 3), 77, np.uint8)
+frames = np.stack([np.roll(one, i, axis=1) for i in range(a.frames)])
+d_in = rip.DeviceBuffer(frames.nbytes).upload(frames)
+d_out = rip.DeviceBuffer(a.frames * a.h * a.w * 4)
+w = rip.gauss_weights(5, 1.0)
+e0, e1 = rip.Event(), rip.Event()
+for i in range(a.launches):
+    if i == a.launches - 1:
+        e0.record()
+    if a.op == "fused":
+        rip.fused_dev(d_in.ptr, d_out.ptr, a.w, a.h, a.frames, rip.FMT_RGB8, 5, w)
+    elif a.op == "sobel":
+        rip.sobel_dev(d_in.ptr, d_out.ptr, a.w, a.h, a.frames, rip.FMT_RGB8)
+    elif a.op == "gray":
+        rip.gray_dev(d_in.ptr, d_out.ptr, a.w, a.h, a.frames, rip.FMT_RGB8)
+e1.record()
+e1.sync()
+ns = e0.elapsed_ns(e1)
+px = a.frames * a.h * a.w
+print(f"{a.op} {a.frames}x{a.w}x{a.h}: last launch {ns/1e3:.1f} us, {px/ns*1e3:.0f} Mpx/s, {px*4/ns:.0f} GB/s algorithmic")
