@@ -25,6 +25,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "rip_common.cuh"
 #include "rip_internal.h"
@@ -53,22 +54,12 @@ struct FusedParams {
 // t = 299r + 587g + 114b via two 2-way dot products per pixel; q = floor(t/1000) = hi32(t * 4294968)
 // (exact for t <= 255000: 4294968*1000 - 2^32 = 704 and 255000*704 < 2^32); t % 1000 == 0 iff the
 // low word of that product is < 2^18 (it is 704*q <= 179520 then, and >= 4294968 otherwise).
-// The 64-bit addend puts 0x4B000000 into the high word: the bits of the float 2^23 + q.
-__device__ __forceinline__ void gray_mul(uint32_t t, uint32_t &lo, float &f)
-{
-    unsigned long long prod;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(prod) : "r"(t), "r"(4294968u), "l"(0x4B00000000000000ull));
-    lo = (uint32_t)prod;
-    f = __uint_as_float((uint32_t)(prod >> 32)) - 8388608.0f;
-}
-
-// t is a multiple of 1000: replay the reference's double evaluation (Comparator.cpp:41)
-__device__ __forceinline__ float gray_slow(uint32_t r, uint32_t g, uint32_t b)
-{
-    const double s = __dadd_rn(__dadd_rn(__dmul_rn(0.299, (double)r), __dmul_rn(0.587, (double)g)),
-                               __dmul_rn(0.114, (double)b));
-    return (float)__double2int_rz(s);
-}
+// Off the multiples of 1000 the reference's double expression (Comparator.cpp:41) truncates to q
+// (it is >= 1e-3 away from an integer, the double rounding error is < 1e-12).  ON a multiple of
+// 1000 the rounding of the three double products decides between q and q-1; since 114*b mod 1000
+// has period 500 > 255, (r,g) determines that b uniquely, so one bit per (r,g) -- tabulated on
+// the host by evaluating the reference expression itself -- says whether the result is q-1.
+__device__ uint32_t d_gray_down[2048];  // bit (r<<8|g): the double evaluation lands below q
 
 template <int CN, bool BGR>
 __device__ __forceinline__ void gray4(const uint32_t *w, float f[4])
@@ -87,21 +78,21 @@ __device__ __forceinline__ void gray4(const uint32_t *w, float f[4])
         t[3] = __dp2a_hi(BC, w[2], __dp2a_lo(zA, w[2], 0u));
     }
 #pragma unroll
-    for (int j = 0; j < 4; j++) gray_mul(t[j], lo[j], f[j]);
-    if (min(min(lo[0], lo[1]), min(lo[2], lo[3])) < (1u << 18)) {  // rare (always on r=g=b greys)
+    for (int j = 0; j < 4; j++) {
+        const unsigned long long prod = (unsigned long long)t[j] * 4294968ull;
+        lo[j] = (uint32_t)prod;
+        f[j] = (float)(uint32_t)(prod >> 32);
+    }
+    if (__builtin_expect(min(min(lo[0], lo[1]), min(lo[2], lo[3])) < (1u << 18), 0)) {  // rare (always on r=g=b greys)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if (lo[j] < (1u << 18)) {
-                uint32_t c0, c1, c2;
-                if constexpr (CN == 4) {
-                    c0 = w[j] & 0xffu; c1 = (w[j] >> 8) & 0xffu; c2 = (w[j] >> 16) & 0xffu;
-                } else {
-                    const unsigned long long s01 = ((unsigned long long)w[1] << 32) | w[0];
-                    const unsigned long long s12 = ((unsigned long long)w[2] << 32) | w[1];
-                    const uint32_t px = j == 0 ? w[0] : j == 1 ? (uint32_t)(s01 >> 24) : j == 2 ? (uint32_t)(s12 >> 16) : (w[2] >> 8);
-                    c0 = px & 0xffu; c1 = (px >> 8) & 0xffu; c2 = (px >> 16) & 0xffu;
-                }
-                f[j] = BGR ? gray_slow(c2, c1, c0) : gray_slow(c0, c1, c2);
+                uint32_t px;  // the pixel's three channel bytes in bits 0..23
+                if constexpr (CN == 4) px = w[j];
+                else px = j == 0 ? w[0] : j == 1 ? __funnelshift_r(w[0], w[1], 24) : j == 2 ? __funnelshift_r(w[1], w[2], 16) : (w[2] >> 8);
+                const uint32_t r = BGR ? (px >> 16) & 0xffu : px & 0xffu, g = (px >> 8) & 0xffu;
+                const uint32_t idx = (r << 8) | g;
+                f[j] -= (float)((__ldg(&d_gray_down[idx >> 5]) >> (idx & 31u)) & 1u);
             }
         }
     }
@@ -138,8 +129,7 @@ __device__ __forceinline__ RawRow<CN> load_row(const uint8_t *p, bool valid)
 }
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int PF = 5;      // rows prefetched ahead ...
-constexpr int UNROLL = 5;  // ... = ring period of the gray rows = unroll factor of the row loop
+constexpr int PF = 5;  // rows prefetched ahead = ring period of the gray rows = unroll factor of the row loop
 
 // Per-warp sliding-window state; lives entirely in registers (all indices are compile-time, and
 // a ring slot only occupies registers while its value is live).
@@ -152,52 +142,64 @@ struct WarpState {
 };
 
 struct Geometry {
-    const uint8_t *in_base;  // frame's input band   (warp-uniform)
-    uint8_t *out_base;       // frame's output band  (warp-uniform)
+    const uint8_t *src;      // this lane's pixels in the input row that is prefetched next
+    uint8_t *dst;            // this lane's pixels in the output row produced next (may point before the
+                             // band during the warm-up rows; only dereferenced for valid rows)
     uint32_t in_pitch;
-    uint32_t soff;           // byte offset of this lane's pixels in the row that is prefetched next
-    int doff;                // byte offset of this lane's pixels in the output row produced next
     int lane, lane_last;
-    bool edge, left_edge, right_edge, in_img, store_lane;
+    bool left_edge, right_edge, in_img, store_lane;
     int ys;                  // first output row of the segment
+    float *scratch;          // this warp's [5][kScratchRow] shared-memory scratch (cold path only)
 };
 
-// Sobel magnitude of one output row from the partial sums of blurred rows yo-1, yo, yo+1.
-__device__ __forceinline__ uint32_t sobel_pack(const float *D0, const float *D1, const float *D2, const float *S0,
-                                               const float *S2)
+// Cold path, out of line: exact replay of the reference's 25-tap sum (GaussianBlur.cpp:236-258) for
+// the pixels inside the guard band.  The warp first parks its five gray rows yb-2..yb+2 in a
+// per-warp shared-memory scratch (row-major, 4 columns per lane, 4 floats of padding each side), so
+// every lane can read its +-2 neighbour columns; the call itself then needs only a few registers.
+// Per flagged component the 25 products are summed ky-major / kx-minor from 0.0f with unfused
+// multiply and add, clamped to [0,255] and truncated -- exactly the reference sequence.
+constexpr int kScratchRow = 128 + 8;
+
+__device__ __noinline__ float4 blur_exact(const float *scratch /* [5][kScratchRow], this warp */, const float *w25,
+                                          float4 b, uint32_t mask, int lane)
 {
-    float q[4];
+    float out[4] = {b.x, b.y, b.z, b.w};
+    const float *base = scratch + 4 + 4 * lane - 2;  // column x-2 of component 0
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const float gx = fmaf(2.f, D1[j], D0[j] + D2[j]);
-        const float gy = S2[j] - S0[j];
-        const float m = sqrt_approx(fmaf(gx, gx, gy * gy));
-        q[j] = fminf(m, 255.f) + kMagic;  // saturate, round half to even: result in the low byte
+        if (mask & (1u << j)) {
+            float acc = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 5; ky++)
+#pragma unroll
+                for (int kx = 0; kx < 5; kx++)
+                    acc = __fadd_rn(acc, __fmul_rn(base[ky * kScratchRow + j + kx], w25[ky * 5 + kx]));
+            out[j] = truncf(fminf(fmaxf(acc, 0.f), 255.f));
+        }
     }
-    const uint32_t q01 = __byte_perm(__float_as_uint(q[0]), __float_as_uint(q[1]), 0x0040);
-    const uint32_t q23 = __byte_perm(__float_as_uint(q[2]), __float_as_uint(q[3]), 0x0040);
-    return __byte_perm(q01, q23, 0x5410);
+    __syncwarp();  // scratch may be rewritten by the next replay
+    return make_float4(out[0], out[1], out[2], out[3]);
 }
 
 // One image row of the sliding window.  PH = (r - r_first) % 5 fixes every ring slot statically.
-template <int PH, int CN, bool BGR, bool BLUR>
+// EDGE = the warp's band touches the left or right image border.
+template <int PH, int CN, bool BGR, bool BLUR, bool EDGE>
 __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Geometry &geo, int r)
 {
     const int W = p.W, H = p.H, lane = geo.lane;
-    // ---- 1. gray of the new row r; prefetch row r+PF (row index clamped to the image) -----------
+    // ---- 1. gray of the new row r; prefetch row r+PF (row index clamped to the rows of the band) --
     float f[4];
     {
         const RawRow<CN> raw = st.pre[PH % PF];
-        st.pre[PH % PF] = load_row<CN>(geo.in_base + geo.soff, geo.in_img);
-        // next prefetch is row clamp(r+PF+1) -- clamped to the rows the input band holds
-        if ((unsigned)(r + PF - p.in_row0) < (unsigned)(p.in_rows - 1)) geo.soff += geo.in_pitch;
+        st.pre[PH % PF] = load_row<CN>(geo.src, geo.in_img);
+        if ((unsigned)(r + PF - p.in_row0) < (unsigned)(p.in_rows - 1)) geo.src += geo.in_pitch;
         gray4<CN, BGR>(raw.w, f);
     }
     float b[4];  // blurred row yb as exact u8 values held in floats; without the blur stage: the gray row
     const int yb = BLUR ? r - 2 : r;
     if constexpr (BLUR) {
         // clamp-to-edge columns (GaussianBlur.cpp:240): x < 0 -> column 0, x >= W -> column W-1
-        if (geo.edge) {
+        if constexpr (EDGE) {
             const float first = __shfl_sync(FULL, f[0], 1);
             const float last = __shfl_sync(FULL, f[3], min(geo.lane_last, 31));
             if (geo.left_edge && lane == 0) f[0] = f[1] = f[2] = f[3] = first;
@@ -218,40 +220,27 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
         const float Vp4 = __shfl_down_sync(FULL, V[0], 1), Vp5 = __shfl_down_sync(FULL, V[1], 1);
         const float c[8] = {Vm2, Vm1, V[0], V[1], V[2], V[3], Vp4, Vp5};
         float d[4];
-        bool slow = false;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const float e2 = c[j] + c[j + 4], e1 = c[j + 1] + c[j + 3];
             const float u = fmaf(p.g2, e2, fmaf(p.g1, e1, fmaf(p.g0, c[j + 2], -0.5f)));  // S~ - 0.5
             const float rr = u + kMagic;  // nearest integer to S~ - 0.5: floor(S~) outside the guard band
             b[j] = rr - kMagic;
-            d[j] = u - b[j];              // frac(S~) - 0.5
-            slow = slow || (fabsf(d[j]) > p.thr);
+            d[j] = fabsf(u - b[j]);       // |frac(S~) - 0.5|
         }
-        if (__any_sync(FULL, slow)) {
-            // exact replay (reference order) for the flagged pixels; rows ky = -2..2 are ages 4..0
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool slow = fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3])) > p.thr;
+        if (__builtin_expect(__any_sync(FULL, slow), 0)) {
+            const uint32_t mask = (d[0] > p.thr ? 1u : 0u) | (d[1] > p.thr ? 2u : 0u) | (d[2] > p.thr ? 4u : 0u) |
+                                  (d[3] > p.thr ? 8u : 0u);
+            // reference row order ky = -2..2 = ages 4..0
 #pragma unroll
-            for (int ky = 0; ky < 5; ky++) {
-                const float *g = st.G[(a + 1 + ky) % 5];
-                const float gm2 = __shfl_up_sync(FULL, g[2], 1), gm1 = __shfl_up_sync(FULL, g[3], 1);
-                const float gp4 = __shfl_down_sync(FULL, g[0], 1), gp5 = __shfl_down_sync(FULL, g[1], 1);
-                const float cc[8] = {gm2, gm1, g[0], g[1], g[2], g[3], gp4, gp5};
-                if (slow) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-#pragma unroll
-                        for (int kx = 0; kx < 5; kx++)
-                            acc[j] = __fadd_rn(acc[j], __fmul_rn(cc[j + kx], p.w[ky * 5 + kx]));
-                }
-            }
-            if (slow) {
-                unsigned n = 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (fabsf(d[j]) > p.thr) { b[j] = truncf(fminf(fmaxf(acc[j], 0.f), 255.f)); n++; }
-                if (p.slow_counter) atomicAdd(p.slow_counter, (unsigned long long)n);
-            }
+            for (int ky = 0; ky < 5; ky++)
+                *reinterpret_cast<float4 *>(geo.scratch + ky * kScratchRow + 4 + 4 * lane) =
+                    make_float4(st.G[(a + 1 + ky) % 5][0], st.G[(a + 1 + ky) % 5][1], st.G[(a + 1 + ky) % 5][2], st.G[(a + 1 + ky) % 5][3]);
+            __syncwarp();
+            const float4 fx = blur_exact(geo.scratch, p.w, make_float4(b[0], b[1], b[2], b[3]), mask, lane);
+            b[0] = fx.x; b[1] = fx.y; b[2] = fx.z; b[3] = fx.w;
+            if (p.slow_counter && mask) atomicAdd(p.slow_counter, (unsigned long long)__popc(mask));
         }
     } else {
 #pragma unroll
@@ -260,7 +249,7 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
 
     // ---- 3. Sobel partial sums of row yb, BORDER_REFLECT_101 in x --------------------------------
     float bl = __shfl_up_sync(FULL, b[3], 1), br = __shfl_down_sync(FULL, b[0], 1);
-    if (geo.edge) {
+    if constexpr (EDGE) {
         if (geo.left_edge && lane == 1) bl = b[1];                 // x = -1 -> x = 1
         if (geo.right_edge && lane == geo.lane_last) br = b[2];    // x = W  -> x = W-2
     }
@@ -275,18 +264,44 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
     }
     // ---- 4. output row yo = yb-1 from blurred rows yo-1, yo, yo+1 --------------------------------
     const int yo = yb - 1;
-    if (yo >= geo.ys) {  // warp-uniform; false only during the warm-up rows of the segment
-        uint32_t packed;
-        if (yo == 0) {            // BORDER_REFLECT_101 in y: row -1 -> row 1
-            packed = sobel_pack(st.Dr[s2], st.Dr[s1], st.Dr[s2], st.Sr[s2], st.Sr[s2]);
-        } else if (yb == H) {     // row H -> row H-2 (this iteration's input row is a dummy)
-            packed = sobel_pack(st.Dr[s0], st.Dr[s1], st.Dr[s0], st.Sr[s0], st.Sr[s0]);
-        } else {
-            packed = sobel_pack(st.Dr[s0], st.Dr[s1], st.Dr[s2], st.Sr[s0], st.Sr[s2]);
+    if (__builtin_expect(yo == 0 || yb == H, 0)) {  // BORDER_REFLECT_101 in y (cold: two rows per frame)
+        if (yo == 0) {        // row -1 -> row 1
+#pragma unroll
+            for (int j = 0; j < 4; j++) { st.Dr[s0][j] = st.Dr[s2][j]; st.Sr[s0][j] = st.Sr[s2][j]; }
+        } else {              // row H -> row H-2 (this iteration's input row was a dummy)
+#pragma unroll
+            for (int j = 0; j < 4; j++) { st.Dr[s2][j] = st.Dr[s0][j]; st.Sr[s2][j] = st.Sr[s0][j]; }
         }
-        if (geo.store_lane) *reinterpret_cast<uint32_t *>(geo.out_base + (uint32_t)geo.doff) = packed;
     }
-    geo.doff += W;
+    if (yo >= geo.ys) {  // warp-uniform; false only during the warm-up rows of the segment
+        float q[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float gx = fmaf(2.f, st.Dr[s1][j], st.Dr[s0][j] + st.Dr[s2][j]);
+            const float gy = st.Sr[s2][j] - st.Sr[s0][j];
+            const float m = sqrt_approx(fmaf(gx, gx, gy * gy));
+            q[j] = fminf(m, 255.f) + kMagic;  // saturate, round half to even: result in the low byte
+        }
+        const uint32_t q01 = __byte_perm(__float_as_uint(q[0]), __float_as_uint(q[1]), 0x0040);
+        const uint32_t q23 = __byte_perm(__float_as_uint(q[2]), __float_as_uint(q[3]), 0x0040);
+        // predicated store (no branch: lanes 0 and 31 are halo lanes and must not diverge here)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}"
+                     :: "l"(geo.dst), "r"(__byte_perm(q01, q23, 0x5410)), "r"((uint32_t)geo.store_lane) : "memory");
+    }
+    geo.dst += W;
+}
+
+template <int CN, bool BGR, bool BLUR, bool EDGE>
+__device__ __forceinline__ void run_segment(WarpState<CN> &st, const FusedParams &p, Geometry &geo, int r, int r_last)
+{
+#define RIP_STEP(PH)                                        \
+    if (r > r_last) break;                                  \
+    step<PH, CN, BGR, BLUR, EDGE>(st, p, geo, r);           \
+    r++;
+    for (;;) {
+        RIP_STEP(0) RIP_STEP(1) RIP_STEP(2) RIP_STEP(3) RIP_STEP(4)
+    }
+#undef RIP_STEP
 }
 
 template <int CN, bool BGR, bool BLUR>
@@ -295,9 +310,11 @@ fused_kernel(const __grid_constant__ FusedParams p)
 {
     constexpr int HALO = BLUR ? 3 : 1;  // input rows above/below an output row
 
+    __shared__ __align__(16) float scratch[BLUR ? kWarpsPerBlock * 5 * kScratchRow : 4];
     Geometry geo;
     geo.lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    geo.scratch = scratch + (BLUR ? warp * 5 * kScratchRow : 0);
     int bid = blockIdx.x;
     const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
     const int seg = bid % p.n_segs;
@@ -312,12 +329,10 @@ fused_kernel(const __grid_constant__ FusedParams p)
     geo.lane_last = (W - xw0) >> 2;              // lane holding pixels W-4..W-1 (may be > 31)
     geo.left_edge = (band == 0);
     geo.right_edge = (geo.lane_last <= 31);
-    geo.edge = geo.left_edge || geo.right_edge;
     geo.ys = p.out_row0 + seg * p.seg_rows;
     const int ye = min(geo.ys + p.seg_rows, p.out_row0 + p.out_rows);
     geo.in_pitch = (uint32_t)W * CN;
-    geo.in_base = p.in + (size_t)frame * p.in_rows * geo.in_pitch;
-    geo.out_base = p.out + (size_t)frame * p.out_rows * W;
+    const uint8_t *in_base = p.in + (size_t)frame * p.in_rows * geo.in_pitch;
     geo.store_lane = (geo.lane >= 1) && (geo.lane <= 30) && geo.in_img;
 
     WarpState<CN> st;
@@ -335,21 +350,14 @@ fused_kernel(const __grid_constant__ FusedParams p)
 #pragma unroll
     for (int i = 0; i < PF; i++) {
         const int rs = min(max(r_first + i - p.in_row0, 0), p.in_rows - 1);
-        st.pre[i] = load_row<CN>(geo.in_base + (uint32_t)rs * geo.in_pitch + xoff, geo.in_img);
+        st.pre[i] = load_row<CN>(in_base + (size_t)rs * geo.in_pitch + xoff, geo.in_img);
     }
-    geo.soff = (uint32_t)min(max(r_first + PF - p.in_row0, 0), p.in_rows - 1) * geo.in_pitch + xoff;
+    geo.src = in_base + (size_t)min(max(r_first + PF - p.in_row0, 0), p.in_rows - 1) * geo.in_pitch + xoff;
     // output row produced by the step of input row r is r - HALO
-    geo.doff = (r_first - HALO - p.out_row0) * W + x;
+    geo.dst = p.out + (size_t)frame * p.out_rows * W + (ptrdiff_t)(r_first - HALO - p.out_row0) * W + x;
 
-    int r = r_first;
-#define RIP_STEP(PH)                                   \
-    if (r > r_last) break;                             \
-    step<PH, CN, BGR, BLUR>(st, p, geo, r);            \
-    r++;
-    for (;;) {
-        RIP_STEP(0) RIP_STEP(1) RIP_STEP(2) RIP_STEP(3) RIP_STEP(4)
-    }
-#undef RIP_STEP
+    if (geo.left_edge || geo.right_edge) run_segment<CN, BGR, BLUR, true>(st, p, geo, r_first, r_last);
+    else run_segment<CN, BGR, BLUR, false>(st, p, geo, r_first, r_last);
 }
 
 }  // namespace
@@ -371,9 +379,8 @@ bool fused_supported(int W, int H, int fmt, int ksize, const uint8_t *d_in, cons
 
 // Guard band for the fast path, and the separable taps that minimise it.  See DESIGN.md
 // ("Exact blur at separable cost") for the derivation:
-//   |S_ref - S| <= 25 u S (24 rounded adds + 25 rounded products, all terms >= 0, u = 2^-24)
-//   |S~    - S| <= 255 * sum|w_ij - g_i g_j|  +  10 u S (separable evaluation with FMAs)
-// with S <= 255 * sum(w).  The kernel compares |frac(S~) - 0.5| against 0.5 - band.
+//   |S_ref - S| <= u * 255 * (sum_i w_i (25 - i) + sum_i w_i)      (sequential fp32 sum, u = 2^-24)
+//   |S~    - S| <= 255 * sum|w_ij - g_i g_j|  +  9 u * 255 * sum_i w_i   (separable FMA evaluation)  The kernel compares |frac(S~) - 0.5| against 0.5 - band.
 bool fused_plan_weights(const float *w25, float g[3], float *thr)
 {
     double sum = 0.0;
@@ -390,9 +397,13 @@ bool fused_plan_weights(const float *w25, float g[3], float *thr)
     for (int ky = -2; ky <= 2; ky++)
         for (int kx = -2; kx <= 2; kx++)
             dev += std::fabs((double)w25[(ky + 2) * 5 + (kx + 2)] - (double)g[std::abs(ky)] * (double)g[std::abs(kx)]);
+    // reference error: acc_k = fl(acc_{k-1} + fl(p_k w_k)); each add errs by <= u*|acc_k| and
+    // acc_k <= 255 * (w_0 + .. + w_k), so the adds contribute <= u * 255 * sum_i w_i * (25 - i);
+    // the 25 rounded products add <= u * 255 * sum(w).  Fast path: <= 9 u * 255 * sum(w).
     const double u = std::ldexp(1.0, -24);
-    const double smax = 255.0 * sum;
-    const double band = 255.0 * dev + (25.0 + 10.0 + 3.0) * u * smax * 1.01 + 1e-6;
+    double cum = 0.0;
+    for (int i = 0; i < 25; i++) cum += (double)w25[i] * (25 - i);
+    const double band = 255.0 * dev + u * 255.0 * (cum + sum + 9.0 * sum) * 1.02 + 1e-6;
     if (band > 0.05) return false;  // weights are not (close to) a symmetric separable kernel
     *thr = (float)(0.5 - band);
     return true;
@@ -413,7 +424,39 @@ static int pick_seg_rows(int out_rows, int n_frames, int n_band_groups, int devi
     return seg;
 }
 
-static unsigned long long *g_slow_counter = nullptr;  // set by rip_debug_set_slow_counter
+static unsigned long long *g_slow_counter = nullptr;  // set by rip_debug_slow_path_stats
+
+// d_gray_down, per device, filled once by evaluating the reference expression (Comparator.cpp:41)
+// in double on the host for the 16 774 (r,g,b) triples whose 299r+587g+114b is a multiple of 1000.
+static int ensure_gray_table(int device)
+{
+    static std::mutex mu;
+    static bool done[64];
+    if (device < 0 || device >= 64) return fail(RIP_EINVAL, "device %d out of range", device);
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[device]) return RIP_OK;
+    static uint32_t bits[2048];
+    static bool built = false;
+    if (!built) {
+        memset(bits, 0, sizeof(bits));
+        for (int r = 0; r < 256; r++)
+            for (int g = 0; g < 256; g++)
+                for (int b = 0; b < 256; b++) {
+                    const int t = 299 * r + 587 * g + 114 * b;
+                    if (t % 1000) continue;
+                    volatile double s = 0.299 * r;  // volatile: no contraction, strict left-to-right doubles
+                    volatile double s2 = 0.587 * g;
+                    volatile double s3 = 0.114 * b;
+                    volatile double sum = s + s2;
+                    sum = sum + s3;
+                    if ((int)sum < t / 1000) bits[(r << 8 | g) >> 5] |= 1u << ((r << 8 | g) & 31);
+                }
+        built = true;
+    }
+    RIP_CUDA(cudaMemcpyToSymbol(d_gray_down, bits, sizeof(bits)));
+    done[device] = true;
+    return RIP_OK;
+}
 
 template <int CN, bool BGR>
 static void launch_t(bool blur, dim3 grid, cudaStream_t s, const FusedParams &p)
@@ -426,6 +469,7 @@ int launch_fused(cudaStream_t s, const uint8_t *d_in, uint8_t *d_out, int W, int
                  bool with_blur, const float *weights25, int in_row0, int in_rows, int out_row0, int out_rows,
                  int device)
 {
+    if (int rc = ensure_gray_table(device)) return rc;
     FusedParams p;
     memset(&p, 0, sizeof(p));
     p.in = d_in; p.out = d_out; p.W = W; p.H = H;
@@ -510,6 +554,7 @@ __global__ void selftest_gray_kernel(unsigned long long *bad)
 
 int fused_selftest(int device, unsigned long long *checked, unsigned long long *mismatches)
 {
+    if (int rc = ensure_gray_table(device)) return rc;
     unsigned long long *d_bad = nullptr;
     RIP_CUDA(cudaMalloc(&d_bad, sizeof(*d_bad)));
     RIP_CUDA(cudaMemset(d_bad, 0, sizeof(*d_bad)));
