@@ -129,70 +129,75 @@ __device__ __forceinline__ RawRow<CN> load_row(const uint8_t *p, bool valid)
 }
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int PF = 5;  // rows prefetched ahead = ring period of the gray rows = unroll factor of the row loop
+constexpr int kRingRow = 128 + 8;  // floats per gray row in the per-warp shared ring (4 pad each side)
 
-// Per-warp sliding-window state; lives entirely in registers (all indices are compile-time, and
-// a ring slot only occupies registers while its value is live).
+// Per-warp sliding-window state, all in registers.  The row loop is NOT unrolled: the whole hot
+// loop is ~3 KB of SASS and stays resident in the per-partition instruction cache (an earlier
+// 5x-unrolled version was instruction-fetch bound, see profiles/).  To make a rolled loop possible
+// the vertical blur runs in accumulate form -- each new gray row is added into the four pending
+// blurred rows with FMAs whose destination is the *next* accumulator, so the shift costs no
+// register moves -- and only the small Sobel ring is shifted explicitly.
 template <int CN>
 struct WarpState {
-    float G[5][4];   // gray rows r-4..r                                   (slot = phase % 5)
-    float Dr[5][4];  // b[x+1]-b[x-1]       of blurred rows; only the last two are live
-    float Sr[5][4];  // b[x-1]+2b[x]+b[x+1] of blurred rows; only the last two are live
-    RawRow<CN> pre[PF];
+    float a0[4], a1[4], a2[4], a3[4];  // partial vertical sums of blurred rows r-2, r-1, r, r+1 (missing rows >= r)
+    float X0[4], X1[4];                // D(yb-2) + 2 D(yb-1)  and  D(yb-1),  D(y) = b[x+1] - b[x-1] of blurred row y
+    float S1[4], S2[4];                // S(yb-1), S(yb-2),    S(y) = b[x-1] + 2 b[x] + b[x+1]
+    RawRow<CN> pre;                    // input row r+1, prefetched one step ahead
 };
 
 struct Geometry {
     const uint8_t *src;      // this lane's pixels in the input row that is prefetched next
     uint8_t *dst;            // this lane's pixels in the output row produced next (may point before the
                              // band during the warm-up rows; only dereferenced for valid rows)
+    float *ring;             // this warp's gray ring [5][kRingRow] in shared memory
     uint32_t in_pitch;
     int lane, lane_last;
-    bool left_edge, right_edge, in_img, store_lane;
+    bool left_edge, right_edge, in_img;
+    uint32_t store_lane;
     int ys;                  // first output row of the segment
-    float *scratch;          // this warp's [5][kScratchRow] shared-memory scratch (cold path only)
+    int slot;                // ring slot of the newest gray row
 };
 
 // Cold path, out of line: exact replay of the reference's 25-tap sum (GaussianBlur.cpp:236-258) for
-// the pixels inside the guard band.  The warp first parks its five gray rows yb-2..yb+2 in a
-// per-warp shared-memory scratch (row-major, 4 columns per lane, 4 floats of padding each side), so
-// every lane can read its +-2 neighbour columns; the call itself then needs only a few registers.
-// Per flagged component the 25 products are summed ky-major / kx-minor from 0.0f with unfused
-// multiply and add, clamped to [0,255] and truncated -- exactly the reference sequence.
-constexpr int kScratchRow = 128 + 8;
-
-__device__ __noinline__ float4 blur_exact(const float *scratch /* [5][kScratchRow], this warp */, const float *w25,
-                                          float4 b, uint32_t mask, int lane)
+// the pixels inside the guard band.  The gray rows yb-2..yb+2 sit in the warp's shared-memory ring
+// (slot_new holds row yb+2), so a lane reads its +-2 neighbour columns directly.  Per flagged
+// component the 25 products are summed ky-major / kx-minor from 0.0f with unfused multiply and
+// add, clamped to [0,255] and truncated -- exactly the reference sequence.
+__device__ __noinline__ float4 blur_exact(const float *ring, int slot_new, const float *w25, float4 b, uint32_t mask, int lane)
 {
+    __syncwarp();  // the newest row was just stored by the other lanes
     float out[4] = {b.x, b.y, b.z, b.w};
-    const float *base = scratch + 4 + 4 * lane - 2;  // column x-2 of component 0
+    const float *base = ring + 4 + 4 * lane - 2;  // column x-2 of component 0
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         if (mask & (1u << j)) {
             float acc = 0.f;
+            int slot = slot_new;
 #pragma unroll
-            for (int ky = 0; ky < 5; ky++)
+            for (int ky = 0; ky < 5; ky++) {
+                slot = slot == 4 ? 0 : slot + 1;  // oldest row first
+                const float *row = base + slot * kRingRow + j;
 #pragma unroll
-                for (int kx = 0; kx < 5; kx++)
-                    acc = __fadd_rn(acc, __fmul_rn(base[ky * kScratchRow + j + kx], w25[ky * 5 + kx]));
+                for (int kx = 0; kx < 5; kx++) acc = __fadd_rn(acc, __fmul_rn(row[kx], w25[ky * 5 + kx]));
+            }
             out[j] = truncf(fminf(fmaxf(acc, 0.f), 255.f));
         }
     }
-    __syncwarp();  // scratch may be rewritten by the next replay
+    __syncwarp();  // the ring slot of the oldest row is overwritten by the next step
     return make_float4(out[0], out[1], out[2], out[3]);
 }
 
-// One image row of the sliding window.  PH = (r - r_first) % 5 fixes every ring slot statically.
-// EDGE = the warp's band touches the left or right image border.
-template <int PH, int CN, bool BGR, bool BLUR, bool EDGE>
+// One image row of the sliding window.  EDGE = the warp's band touches the left/right image border.
+template <int CN, bool BGR, bool BLUR, bool EDGE>
 __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Geometry &geo, int r)
 {
     const int W = p.W, H = p.H, lane = geo.lane;
-    // ---- 1. gray of the new row r; prefetch row r+PF (row index clamped to the rows of the band) --
+    // ---- 1. gray of the new row r; prefetch row r+1 (row index clamped to the rows of the band) ----
     float f[4];
     {
-        const RawRow<CN> raw = st.pre[PH % PF];
-        st.pre[PH % PF] = load_row<CN>(geo.src, geo.in_img);
-        if ((unsigned)(r + PF - p.in_row0) < (unsigned)(p.in_rows - 1)) geo.src += geo.in_pitch;
+        const RawRow<CN> raw = st.pre;
+        if ((unsigned)(r - p.in_row0) < (unsigned)(p.in_rows - 1)) geo.src += geo.in_pitch;
+        st.pre = load_row<CN>(geo.src, geo.in_img);
         gray4<CN, BGR>(raw.w, f);
     }
     float b[4];  // blurred row yb as exact u8 values held in floats; without the blur stage: the gray row
@@ -205,16 +210,18 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
             if (geo.left_edge && lane == 0) f[0] = f[1] = f[2] = f[3] = first;
             if (geo.right_edge && lane > geo.lane_last) f[0] = f[1] = f[2] = f[3] = last;
         }
-        constexpr int a = PH % 5;
-#pragma unroll
-        for (int j = 0; j < 4; j++) st.G[a][j] = f[j];
-        // slots by age: 0 (row r) = a, 1 = a+4, 2 = a+3, 3 = a+2, 4 (row r-4) = a+1   (mod 5)
+        // park the gray row in the shared ring (only the cold exact replay reads it back)
+        geo.slot = geo.slot == 4 ? 0 : geo.slot + 1;
+        *reinterpret_cast<float4 *>(geo.ring + geo.slot * kRingRow + 4 + 4 * lane) = make_float4(f[0], f[1], f[2], f[3]);
+        // vertical pass, accumulate form: row r completes blurred row r-2
         float V[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const float e2 = st.G[a][j] + st.G[(a + 1) % 5][j];
-            const float e1 = st.G[(a + 4) % 5][j] + st.G[(a + 2) % 5][j];
-            V[j] = fmaf(p.g2, e2, fmaf(p.g1, e1, p.g0 * st.G[(a + 3) % 5][j]));
+            V[j] = fmaf(p.g2, f[j], st.a0[j]);
+            st.a0[j] = fmaf(p.g1, f[j], st.a1[j]);
+            st.a1[j] = fmaf(p.g0, f[j], st.a2[j]);
+            st.a2[j] = fmaf(p.g1, f[j], st.a3[j]);
+            st.a3[j] = p.g2 * f[j];
         }
         const float Vm2 = __shfl_up_sync(FULL, V[2], 1), Vm1 = __shfl_up_sync(FULL, V[3], 1);
         const float Vp4 = __shfl_down_sync(FULL, V[0], 1), Vp5 = __shfl_down_sync(FULL, V[1], 1);
@@ -232,13 +239,7 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
         if (__builtin_expect(__any_sync(FULL, slow), 0)) {
             const uint32_t mask = (d[0] > p.thr ? 1u : 0u) | (d[1] > p.thr ? 2u : 0u) | (d[2] > p.thr ? 4u : 0u) |
                                   (d[3] > p.thr ? 8u : 0u);
-            // reference row order ky = -2..2 = ages 4..0
-#pragma unroll
-            for (int ky = 0; ky < 5; ky++)
-                *reinterpret_cast<float4 *>(geo.scratch + ky * kScratchRow + 4 + 4 * lane) =
-                    make_float4(st.G[(a + 1 + ky) % 5][0], st.G[(a + 1 + ky) % 5][1], st.G[(a + 1 + ky) % 5][2], st.G[(a + 1 + ky) % 5][3]);
-            __syncwarp();
-            const float4 fx = blur_exact(geo.scratch, p.w, make_float4(b[0], b[1], b[2], b[3]), mask, lane);
+            const float4 fx = blur_exact(geo.ring, geo.slot, p.w, make_float4(b[0], b[1], b[2], b[3]), mask, lane);
             b[0] = fx.x; b[1] = fx.y; b[2] = fx.z; b[3] = fx.w;
             if (p.slow_counter && mask) atomicAdd(p.slow_counter, (unsigned long long)__popc(mask));
         }
@@ -253,32 +254,32 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
         if (geo.left_edge && lane == 1) bl = b[1];                 // x = -1 -> x = 1
         if (geo.right_edge && lane == geo.lane_last) br = b[2];    // x = W  -> x = W-2
     }
-    constexpr int s0 = (PH + 3) % 5, s1 = (PH + 4) % 5, s2 = PH % 5;  // slots of blurred rows yb-2, yb-1, yb
+    float Dc[4], Sc[4];
     {
         const float e[6] = {bl, b[0], b[1], b[2], b[3], br};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            st.Dr[s2][j] = e[j + 2] - e[j];
-            st.Sr[s2][j] = fmaf(2.f, e[j + 1], e[j] + e[j + 2]);
+            Dc[j] = e[j + 2] - e[j];
+            Sc[j] = fmaf(2.f, e[j + 1], e[j] + e[j + 2]);
         }
     }
-    // ---- 4. output row yo = yb-1 from blurred rows yo-1, yo, yo+1 --------------------------------
+    // ---- 4. output row yo = yb-1:  gx = D(yo-1) + 2 D(yo) + D(yo+1),  gy = S(yo+1) - S(yo-1) ------
     const int yo = yb - 1;
-    if (__builtin_expect(yo == 0 || yb == H, 0)) {  // BORDER_REFLECT_101 in y (cold: two rows per frame)
-        if (yo == 0) {        // row -1 -> row 1
+    if (__builtin_expect(yo == 0 || yb == H, 0)) {  // BORDER_REFLECT_101 in y (two rows per frame)
+        if (yo == 0) {   // row -1 -> row 1:  gx = 2 D(0) + 2 D(1), gy = 0
 #pragma unroll
-            for (int j = 0; j < 4; j++) { st.Dr[s0][j] = st.Dr[s2][j]; st.Sr[s0][j] = st.Sr[s2][j]; }
-        } else {              // row H -> row H-2 (this iteration's input row was a dummy)
+            for (int j = 0; j < 4; j++) { st.X0[j] = fmaf(2.f, st.X1[j], Dc[j]); st.S2[j] = Sc[j]; }
+        } else {         // row H -> row H-2 (this step's input row was a dummy): D(H-2) = X0 - 2 X1
 #pragma unroll
-            for (int j = 0; j < 4; j++) { st.Dr[s2][j] = st.Dr[s0][j]; st.Sr[s2][j] = st.Sr[s0][j]; }
+            for (int j = 0; j < 4; j++) { Dc[j] = fmaf(-2.f, st.X1[j], st.X0[j]); Sc[j] = st.S2[j]; }
         }
     }
     if (yo >= geo.ys) {  // warp-uniform; false only during the warm-up rows of the segment
         float q[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const float gx = fmaf(2.f, st.Dr[s1][j], st.Dr[s0][j] + st.Dr[s2][j]);
-            const float gy = st.Sr[s2][j] - st.Sr[s0][j];
+            const float gx = st.X0[j] + Dc[j];
+            const float gy = Sc[j] - st.S2[j];
             const float m = sqrt_approx(fmaf(gx, gx, gy * gy));
             q[j] = fminf(m, 255.f) + kMagic;  // saturate, round half to even: result in the low byte
         }
@@ -286,7 +287,14 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
         const uint32_t q23 = __byte_perm(__float_as_uint(q[2]), __float_as_uint(q[3]), 0x0040);
         // predicated store (no branch: lanes 0 and 31 are halo lanes and must not diverge here)
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}"
-                     :: "l"(geo.dst), "r"(__byte_perm(q01, q23, 0x5410)), "r"((uint32_t)geo.store_lane) : "memory");
+                     :: "l"(geo.dst), "r"(__byte_perm(q01, q23, 0x5410)), "r"(geo.store_lane) : "memory");
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        st.X0[j] = fmaf(2.f, Dc[j], st.X1[j]);
+        st.X1[j] = Dc[j];
+        st.S2[j] = st.S1[j];
+        st.S1[j] = Sc[j];
     }
     geo.dst += W;
 }
@@ -294,14 +302,8 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
 template <int CN, bool BGR, bool BLUR, bool EDGE>
 __device__ __forceinline__ void run_segment(WarpState<CN> &st, const FusedParams &p, Geometry &geo, int r, int r_last)
 {
-#define RIP_STEP(PH)                                        \
-    if (r > r_last) break;                                  \
-    step<PH, CN, BGR, BLUR, EDGE>(st, p, geo, r);           \
-    r++;
-    for (;;) {
-        RIP_STEP(0) RIP_STEP(1) RIP_STEP(2) RIP_STEP(3) RIP_STEP(4)
-    }
-#undef RIP_STEP
+#pragma unroll 1
+    for (; r <= r_last; r++) step<CN, BGR, BLUR, EDGE>(st, p, geo, r);
 }
 
 template <int CN, bool BGR, bool BLUR>
@@ -310,11 +312,12 @@ fused_kernel(const __grid_constant__ FusedParams p)
 {
     constexpr int HALO = BLUR ? 3 : 1;  // input rows above/below an output row
 
-    __shared__ __align__(16) float scratch[BLUR ? kWarpsPerBlock * 5 * kScratchRow : 4];
+    __shared__ __align__(16) float ring[BLUR ? kWarpsPerBlock * 5 * kRingRow : 4];
     Geometry geo;
     geo.lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    geo.scratch = scratch + (BLUR ? warp * 5 * kScratchRow : 0);
+    geo.ring = ring + (BLUR ? warp * 5 * kRingRow : 0);
+    geo.slot = 0;
     int bid = blockIdx.x;
     const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
     const int seg = bid % p.n_segs;
@@ -333,13 +336,12 @@ fused_kernel(const __grid_constant__ FusedParams p)
     const int ye = min(geo.ys + p.seg_rows, p.out_row0 + p.out_rows);
     geo.in_pitch = (uint32_t)W * CN;
     const uint8_t *in_base = p.in + (size_t)frame * p.in_rows * geo.in_pitch;
-    geo.store_lane = (geo.lane >= 1) && (geo.lane <= 30) && geo.in_img;
+    geo.store_lane = ((geo.lane >= 1) && (geo.lane <= 30) && geo.in_img) ? 1u : 0u;
 
     WarpState<CN> st;
 #pragma unroll
-    for (int i = 0; i < 5; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) st.G[i][j] = st.Dr[i][j] = st.Sr[i][j] = 0.f;
+    for (int j = 0; j < 4; j++)
+        st.a0[j] = st.a1[j] = st.a2[j] = st.a3[j] = st.X0[j] = st.X1[j] = st.S1[j] = st.S2[j] = 0.f;
 
     const int r_first = geo.ys - HALO, r_last = ye - 1 + HALO;
     const uint32_t xoff = geo.in_img ? (uint32_t)x * CN : 0u;
@@ -347,12 +349,8 @@ fused_kernel(const __grid_constant__ FusedParams p)
     // covers every row an output needs, and that it starts at row 0 / ends at row H-1 wherever the
     // clamp-to-edge rule (GaussianBlur.cpp:241) is actually exercised; other clamped rows are
     // read-ahead only and never consumed.
-#pragma unroll
-    for (int i = 0; i < PF; i++) {
-        const int rs = min(max(r_first + i - p.in_row0, 0), p.in_rows - 1);
-        st.pre[i] = load_row<CN>(in_base + (size_t)rs * geo.in_pitch + xoff, geo.in_img);
-    }
-    geo.src = in_base + (size_t)min(max(r_first + PF - p.in_row0, 0), p.in_rows - 1) * geo.in_pitch + xoff;
+    geo.src = in_base + (size_t)min(max(r_first - p.in_row0, 0), p.in_rows - 1) * geo.in_pitch + xoff;
+    st.pre = load_row<CN>(geo.src, geo.in_img);
     // output row produced by the step of input row r is r - HALO
     geo.dst = p.out + (size_t)frame * p.out_rows * W + (ptrdiff_t)(r_first - HALO - p.out_row0) * W + x;
 
