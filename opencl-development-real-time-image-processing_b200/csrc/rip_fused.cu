@@ -27,6 +27,8 @@
 #include <cstring>
 #include <mutex>
 
+#include <cuda.h>
+
 #include "rip_common.cuh"
 #include "rip_internal.h"
 
@@ -113,9 +115,7 @@ struct RawRow {
 template <int CN>
 __device__ __forceinline__ RawRow<CN> load_row(const uint8_t *p, bool valid)
 {
-    RawRow<CN> r;
-#pragma unroll
-    for (int i = 0; i < CN; i++) r.w[i] = 0;
+    RawRow<CN> r;  // lanes outside the image keep stale registers: their pixels are never consumed
     if (valid) {
         if constexpr (CN == 4) {
             const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
@@ -358,6 +358,335 @@ fused_kernel(const __grid_constant__ FusedParams p)
     else run_segment<CN, BGR, BLUR, false>(st, p, geo, r_first, r_last);
 }
 
+
+// =============================================================================================
+// TMA variant (the main path): same arithmetic, but
+//   * a lane owns 8 pixels (a warp 256, of which lanes 1..30 = 240 are outputs), halving the
+//     per-row overheads (shuffles, pointer/branch bookkeeping) per pixel;
+//   * the input rows are staged in shared memory by the Tensor Memory Accelerator: one elected
+//     lane issues a 2-D cp.async.bulk.tensor for a [TR rows x 256 px] box of the warp's column
+//     band into a per-warp double-buffered ring and every lane waits on the stage's mbarrier.
+//     The box is addressed in 32-bit elements, so the band's start (a multiple of 8 pixels, i.e.
+//     of 6 words for RGB) needs no 16-byte alignment; out-of-image columns are zero-filled by the
+//     TMA unit and replaced by the clamp-to-edge fix.  The prefetch is a full tile (4 rows) deep
+//     and costs no registers.
+// =============================================================================================
+constexpr int TR = 4;    // rows per TMA box
+constexpr int NST = 2;   // stages in the per-warp ring
+constexpr int NPX = 8;   // pixels per lane
+constexpr int kBandPx8 = 30 * NPX;       // output pixels per warp per row
+constexpr int kRingRow8 = 32 * NPX + 8;  // floats per gray row in the per-warp ring (4 pad each side)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+// The TMA unit requires the box to START on a 16-byte boundary of the row (measured: any other
+// start raises "illegal instruction"; tools/tma_probe.cu).  With 3 bytes per pixel that means a
+// multiple of 16 pixels, so the RGB box starts 16 px left of the band (the lanes' own halo is 8 px)
+// and is 272 px = 204 words wide; with 4 bytes per pixel 8 px / 256 words suffice.
+struct TmaParams {
+    FusedParams f;
+    int tile_words;    // 32-bit words per box row
+    int stage_words;   // words per ring stage = TR * tile_words rounded up to 128 bytes
+    int box_left_px;   // pixels between the box start and the band start (16 for RGB, 8 for RGBA)
+    int lane0_word;    // word offset of lane 0's pixels inside a box row
+};
+
+template <int CN>
+struct WarpState8 {
+    float a0[NPX], a1[NPX], a2[NPX], a3[NPX];  // partial vertical sums of blurred rows r-2..r+1
+    float X0[NPX], X1[NPX];                    // D(yb-2) + 2 D(yb-1), D(yb-1)
+    float S1[NPX], S2[NPX];                    // S(yb-1), S(yb-2)
+};
+
+struct Geometry8 {
+    uint8_t *dst;        // this lane's pixels in the output row produced next
+    float *ring;         // this warp's gray ring [5][kRingRow8]
+    const uint32_t *tiles;  // this warp's TMA ring [NST][TR][tile_words]
+    uint64_t *bars;      // this warp's NST full barriers
+    int lane, lane_last;
+    bool left_edge, right_edge;
+    uint32_t store_lane;
+    int ys, slot;
+    int t0;              // band-relative source row of tile 0, row 0
+    int k_cur;           // tile the consumer is in (-1 before the first)
+    int tma_x, tma_y0;   // tensor coordinates of tile 0: word column, global row of t0
+};
+
+// exact replay, 8-pixel lanes (see blur_exact); values travel by value so they stay in registers
+struct F8 {
+    float v[NPX];
+};
+
+__device__ __noinline__ F8 blur_exact8(const float *ring, int slot_new, const float *w25, F8 b, uint32_t mask, int lane)
+{
+    __syncwarp();
+    const float *base = ring + 4 + NPX * lane - 2;
+#pragma unroll
+    for (int j = 0; j < NPX; j++) {
+        if (mask & (1u << j)) {
+            float acc = 0.f;
+            int slot = slot_new;
+#pragma unroll
+            for (int ky = 0; ky < 5; ky++) {
+                slot = slot == 4 ? 0 : slot + 1;
+                const float *row = base + slot * kRingRow8 + j;
+#pragma unroll
+                for (int kx = 0; kx < 5; kx++) acc = __fadd_rn(acc, __fmul_rn(row[kx], w25[ky * 5 + kx]));
+            }
+            b.v[j] = truncf(fminf(fmaxf(acc, 0.f), 255.f));
+        }
+    }
+    __syncwarp();
+    return b;
+}
+
+template <int CN, bool BGR, bool BLUR, bool EDGE>
+__device__ __forceinline__ void step8(WarpState8<CN> &st, const TmaParams &tp, const CUtensorMap *map, Geometry8 &geo, int r)
+{
+    const FusedParams &p = tp.f;
+    const int W = p.W, H = p.H, lane = geo.lane;
+    constexpr int NW = NPX * CN / 4;  // words per lane per row
+    // ---- 1. locate row r in the TMA ring (row index clamped to the rows of the band) -------------
+    const int cs = min(max(r - p.in_row0, 0), p.in_rows - 1) - geo.t0;
+    const int k = cs / TR;
+    if (k != geo.k_cur) {  // warp-uniform: entering the next tile
+        if (geo.k_cur >= 0) {
+            __syncwarp();  // every lane is done reading tile k_cur: refill its stage with tile k_cur + NST
+            if (lane == 0) {
+                const int kn = geo.k_cur + NST, stage = geo.k_cur % NST;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(geo.bars + stage, (uint32_t)(TR * tp.tile_words * 4));
+                tma_load_2d(const_cast<uint32_t *>(geo.tiles) + stage * tp.stage_words, map, geo.tma_x, geo.tma_y0 + kn * TR,
+                            geo.bars + stage);
+            }
+        }
+        geo.k_cur = k;
+        mbar_wait(geo.bars + (k % NST), (uint32_t)((k / NST) & 1));
+    }
+    uint32_t raw[NW];
+    {
+        const uint32_t *src = geo.tiles + (k % NST) * tp.stage_words + (cs % TR) * tp.tile_words + tp.lane0_word + NW * lane;
+        if constexpr (NW == 6) {
+            const uint2 v0 = *reinterpret_cast<const uint2 *>(src), v1 = *reinterpret_cast<const uint2 *>(src + 2),
+                        v2 = *reinterpret_cast<const uint2 *>(src + 4);
+            raw[0] = v0.x; raw[1] = v0.y; raw[2] = v1.x; raw[3] = v1.y; raw[4] = v2.x; raw[5] = v2.y;
+        } else {
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(src), v1 = *reinterpret_cast<const uint4 *>(src + 4);
+            raw[0] = v0.x; raw[1] = v0.y; raw[2] = v0.z; raw[3] = v0.w; raw[4] = v1.x; raw[5] = v1.y; raw[6] = v1.z; raw[7] = v1.w;
+        }
+    }
+    float f[NPX];
+    gray4<CN, BGR>(raw, f);
+    gray4<CN, BGR>(raw + NW / 2, f + 4);
+
+    float b[NPX];
+    const int yb = BLUR ? r - 2 : r;
+    if constexpr (BLUR) {
+        if constexpr (EDGE) {  // clamp-to-edge columns (GaussianBlur.cpp:240)
+            const float first = __shfl_sync(FULL, f[0], 1);
+            const float last = __shfl_sync(FULL, f[NPX - 1], min(geo.lane_last, 31));
+            if (geo.left_edge && lane == 0) {
+#pragma unroll
+                for (int j = 0; j < NPX; j++) f[j] = first;
+            }
+            if (geo.right_edge && lane > geo.lane_last) {
+#pragma unroll
+                for (int j = 0; j < NPX; j++) f[j] = last;
+            }
+        }
+        geo.slot = geo.slot == 4 ? 0 : geo.slot + 1;
+        {
+            float4 *rp = reinterpret_cast<float4 *>(geo.ring + geo.slot * kRingRow8 + 4 + NPX * lane);
+            rp[0] = make_float4(f[0], f[1], f[2], f[3]);
+            rp[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+        float c[NPX + 4];
+#pragma unroll
+        for (int j = 0; j < NPX; j++) {
+            c[j + 2] = fmaf(p.g2, f[j], st.a0[j]);
+            st.a0[j] = fmaf(p.g1, f[j], st.a1[j]);
+            st.a1[j] = fmaf(p.g0, f[j], st.a2[j]);
+            st.a2[j] = fmaf(p.g1, f[j], st.a3[j]);
+            st.a3[j] = p.g2 * f[j];
+        }
+        c[0] = __shfl_up_sync(FULL, c[NPX], 1);
+        c[1] = __shfl_up_sync(FULL, c[NPX + 1], 1);
+        c[NPX + 2] = __shfl_down_sync(FULL, c[2], 1);
+        c[NPX + 3] = __shfl_down_sync(FULL, c[3], 1);
+        float d[NPX];
+#pragma unroll
+        for (int j = 0; j < NPX; j++) {
+            const float e2 = c[j] + c[j + 4], e1 = c[j + 1] + c[j + 3];
+            const float u = fmaf(p.g2, e2, fmaf(p.g1, e1, fmaf(p.g0, c[j + 2], -0.5f)));
+            const float rr = u + kMagic;
+            b[j] = rr - kMagic;
+            d[j] = fabsf(u - b[j]);
+        }
+        float dm = d[0];
+#pragma unroll
+        for (int j = 1; j < NPX; j++) dm = fmaxf(dm, d[j]);
+        if (__builtin_expect(__any_sync(FULL, dm > p.thr), 0)) {
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < NPX; j++) mask |= (d[j] > p.thr ? 1u : 0u) << j;
+            F8 bv;
+#pragma unroll
+            for (int j = 0; j < NPX; j++) bv.v[j] = b[j];
+            bv = blur_exact8(geo.ring, geo.slot, p.w, bv, mask, lane);
+#pragma unroll
+            for (int j = 0; j < NPX; j++) b[j] = bv.v[j];
+            if (p.slow_counter && mask) atomicAdd(p.slow_counter, (unsigned long long)__popc(mask));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPX; j++) b[j] = f[j];
+    }
+
+    // ---- Sobel partial sums of row yb, BORDER_REFLECT_101 in x -----------------------------------
+    float e[NPX + 2];
+    e[0] = __shfl_up_sync(FULL, b[NPX - 1], 1);
+    e[NPX + 1] = __shfl_down_sync(FULL, b[0], 1);
+#pragma unroll
+    for (int j = 0; j < NPX; j++) e[j + 1] = b[j];
+    if constexpr (EDGE) {
+        if (geo.left_edge && lane == 1) e[0] = b[1];
+        if (geo.right_edge && lane == geo.lane_last) e[NPX + 1] = b[NPX - 2];
+    }
+    float Dc[NPX], Sc[NPX];
+#pragma unroll
+    for (int j = 0; j < NPX; j++) {
+        Dc[j] = e[j + 2] - e[j];
+        Sc[j] = fmaf(2.f, e[j + 1], e[j] + e[j + 2]);
+    }
+    const int yo = yb - 1;
+    if (__builtin_expect(yo == 0 || yb == H, 0)) {  // BORDER_REFLECT_101 in y
+        if (yo == 0) {
+#pragma unroll
+            for (int j = 0; j < NPX; j++) { st.X0[j] = fmaf(2.f, st.X1[j], Dc[j]); st.S2[j] = Sc[j]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NPX; j++) { Dc[j] = fmaf(-2.f, st.X1[j], st.X0[j]); Sc[j] = st.S2[j]; }
+        }
+    }
+    if (yo >= geo.ys) {
+        uint32_t q[NPX];
+#pragma unroll
+        for (int j = 0; j < NPX; j++) {
+            const float gx = st.X0[j] + Dc[j];
+            const float gy = Sc[j] - st.S2[j];
+            const float m = sqrt_approx(fmaf(gx, gx, gy * gy));
+            q[j] = __float_as_uint(fminf(m, 255.f) + kMagic);
+        }
+        const uint32_t lo = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+        const uint32_t hi = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.v2.u32 [%0], {%1, %2};\n\t}"
+                     ::"l"(geo.dst), "r"(lo), "r"(hi), "r"(geo.store_lane) : "memory");
+    }
+#pragma unroll
+    for (int j = 0; j < NPX; j++) {
+        st.X0[j] = fmaf(2.f, Dc[j], st.X1[j]);
+        st.X1[j] = Dc[j];
+        st.S2[j] = st.S1[j];
+        st.S1[j] = Sc[j];
+    }
+    geo.dst += W;
+}
+
+template <int CN, bool BGR, bool BLUR, bool EDGE>
+__device__ __forceinline__ void run_segment8(WarpState8<CN> &st, const TmaParams &tp, const CUtensorMap *map, Geometry8 &geo, int r,
+                                             int r_last)
+{
+#pragma unroll 1
+    for (; r <= r_last; r++) step8<CN, BGR, BLUR, EDGE>(st, tp, map, geo, r);
+}
+
+template <int CN, bool BGR, bool BLUR>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+fused_tma_kernel(const __grid_constant__ TmaParams tp, const __grid_constant__ CUtensorMap map)
+{
+    constexpr int HALO = BLUR ? 3 : 1;
+    const FusedParams &p = tp.f;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    const int tile_bytes = NST * tp.stage_words * 4;      // multiple of 128
+    Geometry8 geo;
+    geo.lane = threadIdx.x & 31;
+    geo.tiles = reinterpret_cast<const uint32_t *>(smem + warp * tile_bytes);
+    geo.ring = reinterpret_cast<float *>(smem + kWarpsPerBlock * tile_bytes) + warp * (BLUR ? 5 * kRingRow8 : 0);
+    geo.bars = reinterpret_cast<uint64_t *>(smem + kWarpsPerBlock * tile_bytes + (BLUR ? kWarpsPerBlock * 5 * kRingRow8 * 4 : 0)) + warp * NST;
+    geo.slot = 0;
+    geo.k_cur = -1;
+
+    int bid = blockIdx.x;
+    const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
+    const int seg = bid % p.n_segs;
+    const int frame = bid / p.n_segs;
+    const int band = bg * kWarpsPerBlock + warp;
+    if (band >= p.n_bands) return;  // warp-uniform; all synchronisation below is per warp
+
+    const int W = p.W;
+    const int x = band * kBandPx8 - NPX + NPX * geo.lane;
+    const bool in_img = (x >= 0) && (x < W);
+    geo.lane_last = (W - band * kBandPx8) / NPX;
+    geo.left_edge = (band == 0);
+    geo.right_edge = (geo.lane_last <= 31);
+    geo.ys = p.out_row0 + seg * p.seg_rows;
+    const int ye = min(geo.ys + p.seg_rows, p.out_row0 + p.out_rows);
+    geo.store_lane = ((geo.lane >= 1) && (geo.lane <= 30) && in_img) ? 1u : 0u;
+    const int r_first = geo.ys - HALO, r_last = ye - 1 + HALO;
+    geo.t0 = min(max(r_first - p.in_row0, 0), p.in_rows - 1);
+    geo.tma_x = ((band * kBandPx8 - tp.box_left_px) * CN) / 4;  // multiple of 4 words; negative / past-the-end columns are zero-filled
+    geo.tma_y0 = frame * p.in_rows + geo.t0;
+    geo.dst = p.out + (size_t)frame * p.out_rows * W + (ptrdiff_t)(r_first - HALO - p.out_row0) * W + x;
+
+    if (geo.lane == 0) {
+        for (int s = 0; s < NST; s++) mbar_init(geo.bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < NST; s++) {
+            mbar_expect_tx(geo.bars + s, (uint32_t)(TR * tp.tile_words * 4));
+            tma_load_2d(const_cast<uint32_t *>(geo.tiles) + s * tp.stage_words, &map, geo.tma_x, geo.tma_y0 + s * TR, geo.bars + s);
+        }
+    }
+    __syncwarp();
+
+    WarpState8<CN> st;
+#pragma unroll
+    for (int j = 0; j < NPX; j++)
+        st.a0[j] = st.a1[j] = st.a2[j] = st.a3[j] = st.X0[j] = st.X1[j] = st.S1[j] = st.S2[j] = 0.f;
+
+    if (geo.left_edge || geo.right_edge) run_segment8<CN, BGR, BLUR, true>(st, tp, &map, geo, r_first, r_last);
+    else run_segment8<CN, BGR, BLUR, false>(st, tp, &map, geo, r_first, r_last);
+
+    // drain: TMA loads still in flight target this block's shared memory; wait for them before exit
+    for (int kk = geo.k_cur + 1; kk < geo.k_cur + NST; kk++) mbar_wait(geo.bars + (kk % NST), (uint32_t)((kk / NST) & 1));
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -456,6 +785,92 @@ static int ensure_gray_table(int device)
     return RIP_OK;
 }
 
+// ---- TMA variant -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+static bool tma_usable(int W, int cn, const uint8_t *d_in, const uint8_t *d_out)
+{
+    if (getenv("RIP_FUSED_NO_TMA")) return false;
+    if ((W & 7) || W < 8) return false;                         // 8-pixel lanes
+    if (((size_t)W * cn) & 15u) return false;                   // TMA global stride: multiple of 16 bytes
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 7u)) return false;
+    return encode_tiled_fn() != nullptr;
+}
+
+template <int CN, bool BGR>
+static cudaError_t launch_tma_t(bool blur, dim3 grid, size_t smem, cudaStream_t s, const TmaParams &tp, const CUtensorMap &map)
+{
+    auto kern = blur ? fused_tma_kernel<CN, BGR, true> : fused_tma_kernel<CN, BGR, false>;
+    static bool attr_done[2] = {false, false};  // per instantiation (static in a template function)
+    if (!attr_done[blur ? 1 : 0] || true) {      // the attribute is per device: set it every time (cheap)
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done[blur ? 1 : 0] = true;
+    }
+    kern<<<grid, kWarpsPerBlock * 32, smem, s>>>(tp, map);
+    return cudaSuccess;
+}
+
+static int launch_fused_tma(cudaStream_t s, FusedParams p, int n_frames, int fmt, bool with_blur, int device)
+{
+    const int cn = (fmt == RIP_FMT_RGB8 || fmt == RIP_FMT_BGR8) ? 3 : 4;
+    TmaParams tp;
+    tp.box_left_px = cn == 3 ? 16 : NPX;
+    tp.tile_words = cn == 3 ? 204 : 256;
+    tp.lane0_word = (tp.box_left_px - NPX) * cn / 4;
+    tp.stage_words = ((TR * tp.tile_words * 4 + 127) / 128) * 128 / 4;
+    p.n_bands = (p.W + kBandPx8 - 1) / kBandPx8;
+    p.n_band_groups = (p.n_bands + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    p.seg_rows = pick_seg_rows(p.out_rows, n_frames, p.n_band_groups, device);
+    p.n_segs = (p.out_rows + p.seg_rows - 1) / p.seg_rows;
+    tp.f = p;
+
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)p.W * cn / 4, (cuuint64_t)n_frames * p.in_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)p.W * cn};
+    const cuuint32_t box[2] = {(cuuint32_t)tp.tile_words, (cuuint32_t)TR};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode_tiled_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t *>(p.in), gdim, gstride, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(RIP_EINVAL, "rip_fused: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+    const size_t smem = (size_t)kWarpsPerBlock * NST * tp.stage_words * 4 + (with_blur ? (size_t)kWarpsPerBlock * 5 * kRingRow8 * 4 : 0) +
+                        (size_t)kWarpsPerBlock * NST * 8;
+    const long long blocks = (long long)n_frames * p.n_segs * p.n_band_groups;
+    if (blocks <= 0 || blocks > 0x7fffffffLL) return fail(RIP_EINVAL, "rip_fused: grid of %lld blocks is out of range", blocks);
+    const dim3 grid((unsigned)blocks);
+    cudaError_t e = cudaSuccess;
+    switch (fmt) {
+    case RIP_FMT_RGB8:  e = launch_tma_t<3, false>(with_blur, grid, smem, s, tp, map); break;
+    case RIP_FMT_BGR8:  e = launch_tma_t<3, true>(with_blur, grid, smem, s, tp, map); break;
+    case RIP_FMT_RGBA8: e = launch_tma_t<4, false>(with_blur, grid, smem, s, tp, map); break;
+    case RIP_FMT_BGRA8: e = launch_tma_t<4, true>(with_blur, grid, smem, s, tp, map); break;
+    default: return fail(RIP_EINVAL, "rip_fused: unsupported input format %d", fmt);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "fused_tma_kernel setup", __FILE__, __LINE__);
+    RIP_LAUNCH_CHECK();
+    return RIP_OK;
+}
+
 template <int CN, bool BGR>
 static void launch_t(bool blur, dim3 grid, cudaStream_t s, const FusedParams &p)
 {
@@ -483,6 +898,10 @@ int launch_fused(cudaStream_t s, const uint8_t *d_in, uint8_t *d_out, int W, int
             return fail(RIP_EUNSUPPORTED, "rip_fused: weights are not a non-negative symmetric separable 5x5 kernel");
         p.g0 = g[0]; p.g1 = g[1]; p.g2 = g[2];
         memcpy(p.w, weights25, sizeof(float) * 25);
+    }
+    {
+        const int cn = (fmt == RIP_FMT_RGB8 || fmt == RIP_FMT_BGR8) ? 3 : 4;
+        if (tma_usable(W, cn, d_in, d_out)) return launch_fused_tma(s, p, n_frames, fmt, with_blur, device);
     }
     const long long blocks = (long long)n_frames * p.n_segs * p.n_band_groups;
     if (blocks <= 0 || blocks > 0x7fffffffLL) return fail(RIP_EINVAL, "rip_fused: grid of %lld blocks is out of range", blocks);

@@ -132,7 +132,8 @@ def test_sobel_gray_input_matches_opencv_goldens(ctx, golden_cv2_sobel, golden_i
             _eq(ctx.process(golden_images[k + ".imread_gray"], rip.OP_EDGE, rip.FMT_GRAY8), v, k)
 
 
-@pytest.mark.parametrize("shape", [(2, 4), (2, 8), (5, 12), (37, 120), (37, 124), (64, 128), (33, 244), (75, 75), (19, 241)])
+@pytest.mark.parametrize("shape", [(2, 4), (2, 8), (5, 12), (37, 120), (37, 124), (64, 128), (33, 244), (75, 75), (19, 241),
+                                   (2, 16), (31, 240), (17, 256), (40, 496)])
 @pytest.mark.parametrize("fmt,cn", [(rip.FMT_RGB8, 3), (rip.FMT_RGBA8, 4), (rip.FMT_BGR8, 3)])
 def test_sobel_colour_input(ctx, oracle, shape, fmt, cn):
     img = synth_frame("uniform", shape[0], shape[1], 21, cn)
@@ -153,7 +154,9 @@ def test_sobel_config3_1080p_batch(ctx, oracle):
 
 
 # ---- fused gray -> blur -> Sobel (configs 4, 5) ------------------------------------------------
-FUSED_SHAPES = [(2, 4), (3, 8), (7, 12), (16, 120), (40, 124), (9, 128), (70, 244), (130, 364), (300, 480), (64, 1920)]
+# widths with W*3 % 16 == 0 take the TMA kernel (8-pixel lanes), other multiples of 4 the LDG kernel
+FUSED_SHAPES = [(2, 4), (3, 8), (7, 12), (16, 120), (40, 124), (9, 128), (70, 244), (130, 364), (300, 480), (64, 1920),
+                (2, 16), (5, 16), (9, 32), (41, 240), (33, 256), (64, 496), (23, 272), (300, 16)]
 
 
 @pytest.mark.parametrize("shape", FUSED_SHAPES)
@@ -213,6 +216,25 @@ def test_fused_adversarial_frames(ctx, oracle, sigma):
     _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w), "fused colour ramps")
 
 
+def test_fused_ldg_and_tma_kernels_agree(oracle, monkeypatch):
+    """The LDG kernel (fallback for widths TMA cannot address) must match on a TMA-capable shape too."""
+    h, wd = 120, 496
+    img = synth_frame("uniform", h, wd, 77)
+    w = rip.gauss_weights(5, 1.0)
+    want = oracle.fused(img, 5, weights=w, threads=0)
+    d_in = rip.DeviceBuffer(img.nbytes).upload(img)
+    d_out = rip.DeviceBuffer(h * wd)
+    outs = []
+    for no_tma in (False, True):
+        if no_tma:
+            monkeypatch.setenv("RIP_FUSED_NO_TMA", "1")
+        rip.lib().rip_memset_device_async(0, d_out.ptr, 0, h * wd, None)
+        rip.fused_dev(d_in.ptr, d_out.ptr, wd, h, 1, rip.FMT_RGB8, 5, w)
+        outs.append(d_out.download((h, wd)))
+    _eq(outs[0], want, "TMA kernel")
+    _eq(outs[1], want, "LDG kernel")
+
+
 def test_fused_guard_band_statistics():
     """The exact replay must actually trigger (flat frames: always) yet stay rare on noise."""
     w = rip.gauss_weights(5, 1.0)
@@ -227,8 +249,9 @@ def test_fused_guard_band_statistics():
         assert lo <= frac <= hi, (kind, frac)
 
 
-def test_fused_row_bands_equal_whole_frame(ctx, oracle):
-    h, wd = 200, 360
+@pytest.mark.parametrize("wd", [360, 368])  # LDG kernel / TMA kernel
+def test_fused_row_bands_equal_whole_frame(ctx, oracle, wd):
+    h = 200
     img = synth_frame("uniform", h, wd, 81)
     w = rip.gauss_weights(5, 1.0)
     whole = oracle.fused(img, 5, weights=w, threads=0)
