@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "librip_cuda.so")
+# RIP_LIB_PATH lets A/B experiments load an alternative build of the same library (tools/ab/*.so)
+LIB_PATH = os.environ.get("RIP_LIB_PATH") or os.path.join(_PKG, "librip_cuda.so")
 
 # ---- constants (include/rip_cuda.h) ----
 FMT_GRAY8, FMT_RGB8, FMT_RGBA8, FMT_BGR8, FMT_BGRA8 = 1, 3, 4, 5, 6

@@ -56,7 +56,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
         glob.glob(os.path.join(INCLUDE, "*.h"))
     if force or _stale(LIB_CUDA, deps):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", _host_cxx(), "-o", LIB_CUDA, *srcs]
+        extra = os.environ.get("RIP_NVCC_DEFS", "").split()
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-ccbin", _host_cxx(), "-o", os.environ.get("RIP_LIB_OUT", LIB_CUDA), *srcs]
         res = subprocess.run(cmd, capture_output=True, text=True)
         log = res.stdout + res.stderr
         with open(os.path.join(PKG, "build_cuda.log"), "w") as f:

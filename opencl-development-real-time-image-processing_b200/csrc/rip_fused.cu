@@ -32,6 +32,13 @@
 #include "rip_common.cuh"
 #include "rip_internal.h"
 
+#ifndef RIP_LDG_PF
+#define RIP_LDG_PF 1
+#endif
+#ifndef RIP_LDG_MINBLOCKS
+#define RIP_LDG_MINBLOCKS 6
+#endif
+
 namespace rip {
 
 namespace {
@@ -85,7 +92,8 @@ __device__ __forceinline__ void gray4(const uint32_t *w, float f[4])
         lo[j] = (uint32_t)prod;
         f[j] = (float)(uint32_t)(prod >> 32);
     }
-    if (__builtin_expect(min(min(lo[0], lo[1]), min(lo[2], lo[3])) < (1u << 18), 0)) {  // rare (always on r=g=b greys)
+    // warp-uniform test (one vote) so the warp stays converged for the shuffles that follow
+    if (__builtin_expect(__any_sync(0xffffffffu, min(min(lo[0], lo[1]), min(lo[2], lo[3])) < (1u << 18)), 0)) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if (lo[j] < (1u << 18)) {
@@ -143,6 +151,9 @@ struct WarpState {
     float X0[4], X1[4];                // D(yb-2) + 2 D(yb-1)  and  D(yb-1),  D(y) = b[x+1] - b[x-1] of blurred row y
     float S1[4], S2[4];                // S(yb-1), S(yb-2),    S(y) = b[x-1] + 2 b[x] + b[x+1]
     RawRow<CN> pre;                    // input row r+1, prefetched one step ahead
+#if RIP_LDG_PF == 2
+    RawRow<CN> pre2;                   // input row r+2
+#endif
 };
 
 struct Geometry {
@@ -150,12 +161,12 @@ struct Geometry {
     uint8_t *dst;            // this lane's pixels in the output row produced next (may point before the
                              // band during the warm-up rows; only dereferenced for valid rows)
     float *ring;             // this warp's gray ring [5][kRingRow] in shared memory
+    float *ring_cur;         // row of the ring holding the newest gray row (this lane's 4 columns)
     uint32_t in_pitch;
     int lane, lane_last;
     bool left_edge, right_edge, in_img;
     uint32_t store_lane;
     int ys;                  // first output row of the segment
-    int slot;                // ring slot of the newest gray row
 };
 
 // Cold path, out of line: exact replay of the reference's 25-tap sum (GaussianBlur.cpp:236-258) for
@@ -187,8 +198,13 @@ __device__ __noinline__ float4 blur_exact(const float *ring, int slot_new, const
     return make_float4(out[0], out[1], out[2], out[3]);
 }
 
-// One image row of the sliding window.  EDGE = the warp's band touches the left/right image border.
-template <int CN, bool BGR, bool BLUR, bool EDGE>
+// One image row of the sliding window.
+//   EDGE    the warp's band touches the left/right image border (clamp / reflect fix-ups in x)
+//   STORE   the step produces an output row (false for the warm-up rows of a segment)
+//   SPECIAL the step may be the first or last row of the frame (BORDER_REFLECT_101 in y); only the
+//           first and last storing step of a segment are instantiated with it, so the main loop
+//           carries no per-row border checks
+template <int CN, bool BGR, bool BLUR, bool EDGE, bool STORE, bool SPECIAL>
 __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Geometry &geo, int r)
 {
     const int W = p.W, H = p.H, lane = geo.lane;
@@ -196,8 +212,14 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
     float f[4];
     {
         const RawRow<CN> raw = st.pre;
+#if RIP_LDG_PF == 2
+        st.pre = st.pre2;
+        if ((unsigned)(r + 1 - p.in_row0) < (unsigned)(p.in_rows - 1)) geo.src += geo.in_pitch;
+        st.pre2 = load_row<CN>(geo.src, geo.in_img);
+#else
         if ((unsigned)(r - p.in_row0) < (unsigned)(p.in_rows - 1)) geo.src += geo.in_pitch;
         st.pre = load_row<CN>(geo.src, geo.in_img);
+#endif
         gray4<CN, BGR>(raw.w, f);
     }
     float b[4];  // blurred row yb as exact u8 values held in floats; without the blur stage: the gray row
@@ -211,8 +233,9 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
             if (geo.right_edge && lane > geo.lane_last) f[0] = f[1] = f[2] = f[3] = last;
         }
         // park the gray row in the shared ring (only the cold exact replay reads it back)
-        geo.slot = geo.slot == 4 ? 0 : geo.slot + 1;
-        *reinterpret_cast<float4 *>(geo.ring + geo.slot * kRingRow + 4 + 4 * lane) = make_float4(f[0], f[1], f[2], f[3]);
+        geo.ring_cur += kRingRow;
+        if (geo.ring_cur == geo.ring + 5 * kRingRow + 4 + 4 * lane) geo.ring_cur -= 5 * kRingRow;
+        *reinterpret_cast<float4 *>(geo.ring_cur) = make_float4(f[0], f[1], f[2], f[3]);
         // vertical pass, accumulate form: row r completes blurred row r-2
         float V[4];
 #pragma unroll
@@ -239,7 +262,8 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
         if (__builtin_expect(__any_sync(FULL, slow), 0)) {
             const uint32_t mask = (d[0] > p.thr ? 1u : 0u) | (d[1] > p.thr ? 2u : 0u) | (d[2] > p.thr ? 4u : 0u) |
                                   (d[3] > p.thr ? 8u : 0u);
-            const float4 fx = blur_exact(geo.ring, geo.slot, p.w, make_float4(b[0], b[1], b[2], b[3]), mask, lane);
+            const int slot = (int)(geo.ring_cur - (geo.ring + 4 + 4 * lane)) / kRingRow;
+            const float4 fx = blur_exact(geo.ring, slot, p.w, make_float4(b[0], b[1], b[2], b[3]), mask, lane);
             b[0] = fx.x; b[1] = fx.y; b[2] = fx.z; b[3] = fx.w;
             if (p.slow_counter && mask) atomicAdd(p.slow_counter, (unsigned long long)__popc(mask));
         }
@@ -264,17 +288,17 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
         }
     }
     // ---- 4. output row yo = yb-1:  gx = D(yo-1) + 2 D(yo) + D(yo+1),  gy = S(yo+1) - S(yo-1) ------
-    const int yo = yb - 1;
-    if (__builtin_expect(yo == 0 || yb == H, 0)) {  // BORDER_REFLECT_101 in y (two rows per frame)
-        if (yo == 0) {   // row -1 -> row 1:  gx = 2 D(0) + 2 D(1), gy = 0
+    if constexpr (SPECIAL) {  // BORDER_REFLECT_101 in y
+        if (yb == 1) {        // output row 0: row -1 -> row 1:  gx = 2 D(0) + 2 D(1), gy = 0
 #pragma unroll
             for (int j = 0; j < 4; j++) { st.X0[j] = fmaf(2.f, st.X1[j], Dc[j]); st.S2[j] = Sc[j]; }
-        } else {         // row H -> row H-2 (this step's input row was a dummy): D(H-2) = X0 - 2 X1
+        }
+        if (yb == H) {        // output row H-1: row H -> row H-2 (this step's input row was a dummy): D(H-2) = X0 - 2 X1
 #pragma unroll
             for (int j = 0; j < 4; j++) { Dc[j] = fmaf(-2.f, st.X1[j], st.X0[j]); Sc[j] = st.S2[j]; }
         }
     }
-    if (yo >= geo.ys) {  // warp-uniform; false only during the warm-up rows of the segment
+    if constexpr (STORE) {
         float q[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -299,15 +323,27 @@ __device__ __forceinline__ void step(WarpState<CN> &st, const FusedParams &p, Ge
     geo.dst += W;
 }
 
+#ifndef RIP_MAIN_UNROLL
+#define RIP_MAIN_UNROLL 1
+#endif
+constexpr int kMainUnroll = RIP_MAIN_UNROLL;
+
 template <int CN, bool BGR, bool BLUR, bool EDGE>
 __device__ __forceinline__ void run_segment(WarpState<CN> &st, const FusedParams &p, Geometry &geo, int r, int r_last)
 {
+    constexpr int HALO = BLUR ? 3 : 1;
+    const int r_store = geo.ys + HALO;  // first step that produces an output row
 #pragma unroll 1
-    for (; r <= r_last; r++) step<CN, BGR, BLUR, EDGE>(st, p, geo, r);
+    for (; r < r_store; r++) step<CN, BGR, BLUR, EDGE, false, false>(st, p, geo, r);   // warm-up rows
+    step<CN, BGR, BLUR, EDGE, true, true>(st, p, geo, r);                              // may be frame row 0 (and H-1)
+    r++;
+#pragma unroll kMainUnroll
+    for (; r < r_last; r++) step<CN, BGR, BLUR, EDGE, true, false>(st, p, geo, r);     // main loop: no border checks
+    if (r == r_last) step<CN, BGR, BLUR, EDGE, true, true>(st, p, geo, r);             // may be frame row H-1
 }
 
 template <int CN, bool BGR, bool BLUR>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, RIP_LDG_MINBLOCKS)
 fused_kernel(const __grid_constant__ FusedParams p)
 {
     constexpr int HALO = BLUR ? 3 : 1;  // input rows above/below an output row
@@ -317,7 +353,7 @@ fused_kernel(const __grid_constant__ FusedParams p)
     geo.lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     geo.ring = ring + (BLUR ? warp * 5 * kRingRow : 0);
-    geo.slot = 0;
+    geo.ring_cur = geo.ring + 4 + 4 * geo.lane;
     int bid = blockIdx.x;
     const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
     const int seg = bid % p.n_segs;
@@ -351,6 +387,10 @@ fused_kernel(const __grid_constant__ FusedParams p)
     // read-ahead only and never consumed.
     geo.src = in_base + (size_t)min(max(r_first - p.in_row0, 0), p.in_rows - 1) * geo.in_pitch + xoff;
     st.pre = load_row<CN>(geo.src, geo.in_img);
+#if RIP_LDG_PF == 2
+    if ((unsigned)(r_first - p.in_row0) < (unsigned)(p.in_rows - 1)) geo.src += geo.in_pitch;
+    st.pre2 = load_row<CN>(geo.src, geo.in_img);
+#endif
     // output row produced by the step of input row r is r - HALO
     geo.dst = p.out + (size_t)frame * p.out_rows * W + (ptrdiff_t)(r_first - HALO - p.out_row0) * W + x;
 
@@ -360,22 +400,22 @@ fused_kernel(const __grid_constant__ FusedParams p)
 
 
 // =============================================================================================
-// TMA variant (the main path): same arithmetic, but
-//   * a lane owns 8 pixels (a warp 256, of which lanes 1..30 = 240 are outputs), halving the
-//     per-row overheads (shuffles, pointer/branch bookkeeping) per pixel;
-//   * the input rows are staged in shared memory by the Tensor Memory Accelerator: one elected
-//     lane issues a 2-D cp.async.bulk.tensor for a [TR rows x 256 px] box of the warp's column
-//     band into a per-warp double-buffered ring and every lane waits on the stage's mbarrier.
-//     The box is addressed in 32-bit elements, so the band's start (a multiple of 8 pixels, i.e.
-//     of 6 words for RGB) needs no 16-byte alignment; out-of-image columns are zero-filled by the
-//     TMA unit and replaced by the clamp-to-edge fix.  The prefetch is a full tile (4 rows) deep
-//     and costs no registers.
+// TMA variant (the main path): same arithmetic and the same rolled row loop, but the input rows are
+// staged in shared memory by the Tensor Memory Accelerator instead of per-lane global loads:
+//   * one elected lane issues a 2-D cp.async.bulk.tensor for a [TR rows x band] box of the warp's
+//     column band into a per-warp, double-buffered ring; every lane waits on the stage's mbarrier
+//     and then reads its own pixels with shared-memory loads.  The prefetch is 1-2 tiles (4-8 rows)
+//     deep and costs no registers, so DRAM latency is off the critical path.
+//   * the tensor is addressed in 32-bit elements; the TMA unit requires a box to START on a 16-byte
+//     boundary of the row (measured: any other start raises "illegal instruction",
+//     tools/tma_probe.cu).  For 3-byte pixels that is a multiple of 16 pixels, so the RGB box starts
+//     at the band start rounded down to 16 px and is wide enough for the worst rounding; columns
+//     outside the image are zero-filled by the TMA unit and replaced by the clamp-to-edge fix.
+//   * NPX = pixels per lane: 4 (default) or 8 (fewer shuffles per pixel but a loop body that no
+//     longer fits the instruction cache; kept for experiments, RIP_FUSED_NPX=8).
 // =============================================================================================
 constexpr int TR = 4;    // rows per TMA box
 constexpr int NST = 2;   // stages in the per-warp ring
-constexpr int NPX = 8;   // pixels per lane
-constexpr int kBandPx8 = 30 * NPX;       // output pixels per warp per row
-constexpr int kRingRow8 = 32 * NPX + 8;  // floats per gray row in the per-warp ring (4 pad each side)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -404,46 +444,46 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
                  ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
-// The TMA unit requires the box to START on a 16-byte boundary of the row (measured: any other
-// start raises "illegal instruction"; tools/tma_probe.cu).  With 3 bytes per pixel that means a
-// multiple of 16 pixels, so the RGB box starts 16 px left of the band (the lanes' own halo is 8 px)
-// and is 272 px = 204 words wide; with 4 bytes per pixel 8 px / 256 words suffice.
 struct TmaParams {
     FusedParams f;
     int tile_words;    // 32-bit words per box row
     int stage_words;   // words per ring stage = TR * tile_words rounded up to 128 bytes
-    int box_left_px;   // pixels between the box start and the band start (16 for RGB, 8 for RGBA)
-    int lane0_word;    // word offset of lane 0's pixels inside a box row
 };
 
-template <int CN>
-struct WarpState8 {
+template <int NPX>
+struct WarpStateT {
     float a0[NPX], a1[NPX], a2[NPX], a3[NPX];  // partial vertical sums of blurred rows r-2..r+1
     float X0[NPX], X1[NPX];                    // D(yb-2) + 2 D(yb-1), D(yb-1)
     float S1[NPX], S2[NPX];                    // S(yb-1), S(yb-2)
 };
 
-struct Geometry8 {
-    uint8_t *dst;        // this lane's pixels in the output row produced next
-    float *ring;         // this warp's gray ring [5][kRingRow8]
-    const uint32_t *tiles;  // this warp's TMA ring [NST][TR][tile_words]
-    uint64_t *bars;      // this warp's NST full barriers
+struct GeometryT {
+    uint8_t *dst;            // this lane's pixels in the output row produced next
+    float *ring;             // this warp's gray ring [5][32 * NPX + 8]
+    float *ring_cur;         // this lane's columns in the ring row of the newest gray row
+    const uint32_t *tiles;   // this warp's TMA ring [NST][stage_words]
+    const uint32_t *src;     // this lane's words in the ring row of the input row consumed next
+    uint64_t *bars;          // this warp's NST full barriers
     int lane, lane_last;
     bool left_edge, right_edge;
     uint32_t store_lane;
-    int ys, slot;
-    int t0;              // band-relative source row of tile 0, row 0
-    int k_cur;           // tile the consumer is in (-1 before the first)
-    int tma_x, tma_y0;   // tensor coordinates of tile 0: word column, global row of t0
+    int ys;
+    int lane_word;           // word offset of this lane's pixels inside a box row
+    int row_in_tile;         // row of the current tile that the next step consumes
+    int k_cur;               // tile the consumer is in
+    int tma_x, tma_y0;       // tensor coordinates of tile 0: word column, global row
 };
 
-// exact replay, 8-pixel lanes (see blur_exact); values travel by value so they stay in registers
-struct F8 {
+// exact replay (see blur_exact); values travel by value so they stay in registers
+template <int NPX>
+struct FN {
     float v[NPX];
 };
 
-__device__ __noinline__ F8 blur_exact8(const float *ring, int slot_new, const float *w25, F8 b, uint32_t mask, int lane)
+template <int NPX>
+__device__ __noinline__ FN<NPX> blur_exact_n(const float *ring, int slot_new, const float *w25, FN<NPX> b, uint32_t mask, int lane)
 {
+    constexpr int kRow = 32 * NPX + 8;
     __syncwarp();
     const float *base = ring + 4 + NPX * lane - 2;
 #pragma unroll
@@ -454,7 +494,7 @@ __device__ __noinline__ F8 blur_exact8(const float *ring, int slot_new, const fl
 #pragma unroll
             for (int ky = 0; ky < 5; ky++) {
                 slot = slot == 4 ? 0 : slot + 1;
-                const float *row = base + slot * kRingRow8 + j;
+                const float *row = base + slot * kRow + j;
 #pragma unroll
                 for (int kx = 0; kx < 5; kx++) acc = __fadd_rn(acc, __fmul_rn(row[kx], w25[ky * 5 + kx]));
             }
@@ -465,44 +505,58 @@ __device__ __noinline__ F8 blur_exact8(const float *ring, int slot_new, const fl
     return b;
 }
 
-template <int CN, bool BGR, bool BLUR, bool EDGE>
-__device__ __forceinline__ void step8(WarpState8<CN> &st, const TmaParams &tp, const CUtensorMap *map, Geometry8 &geo, int r)
+// Advance to the next tile of the ring: refill the stage just left, wait for the one entered.  Out
+// of line and by value (it runs once per TR rows): returns the new tile index; the caller rebuilds
+// its row pointer from it.
+__device__ __noinline__ int tma_next_tile(const uint32_t *tiles, uint64_t *bars, const CUtensorMap *map, int k_cur, int tma_x, int tma_y0,
+                                          int tile_words, int stage_words, int lane)
+{
+    __syncwarp();  // every lane is done reading tile k_cur
+    if (lane == 0) {
+        const int kn = k_cur + NST, stage = k_cur % NST;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bars + stage, (uint32_t)(TR * tile_words * 4));
+        tma_load_2d(const_cast<uint32_t *>(tiles) + stage * stage_words, map, tma_x, tma_y0 + kn * TR, bars + stage);
+    }
+    k_cur++;
+    mbar_wait(bars + (k_cur % NST), (uint32_t)((k_cur / NST) & 1));
+    return k_cur;
+}
+
+template <int NPX, int CN, bool BGR, bool BLUR, bool EDGE, bool STORE, bool SPECIAL>
+__device__ __forceinline__ void step_t(WarpStateT<NPX> &st, const TmaParams &tp, const CUtensorMap *map, GeometryT &geo, int r)
 {
     const FusedParams &p = tp.f;
     const int W = p.W, H = p.H, lane = geo.lane;
-    constexpr int NW = NPX * CN / 4;  // words per lane per row
-    // ---- 1. locate row r in the TMA ring (row index clamped to the rows of the band) -------------
-    const int cs = min(max(r - p.in_row0, 0), p.in_rows - 1) - geo.t0;
-    const int k = cs / TR;
-    if (k != geo.k_cur) {  // warp-uniform: entering the next tile
-        if (geo.k_cur >= 0) {
-            __syncwarp();  // every lane is done reading tile k_cur: refill its stage with tile k_cur + NST
-            if (lane == 0) {
-                const int kn = geo.k_cur + NST, stage = geo.k_cur % NST;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(geo.bars + stage, (uint32_t)(TR * tp.tile_words * 4));
-                tma_load_2d(const_cast<uint32_t *>(geo.tiles) + stage * tp.stage_words, map, geo.tma_x, geo.tma_y0 + kn * TR,
-                            geo.bars + stage);
-            }
-        }
-        geo.k_cur = k;
-        mbar_wait(geo.bars + (k % NST), (uint32_t)((k / NST) & 1));
-    }
+    constexpr int NW = NPX * CN / 4;        // words per lane per row
+    constexpr int kRow = 32 * NPX + 8;      // floats per gray-ring row
+    // ---- 1. this lane's pixels of row r from the TMA ring ----------------------------------------
     uint32_t raw[NW];
-    {
-        const uint32_t *src = geo.tiles + (k % NST) * tp.stage_words + (cs % TR) * tp.tile_words + tp.lane0_word + NW * lane;
-        if constexpr (NW == 6) {
-            const uint2 v0 = *reinterpret_cast<const uint2 *>(src), v1 = *reinterpret_cast<const uint2 *>(src + 2),
-                        v2 = *reinterpret_cast<const uint2 *>(src + 4);
-            raw[0] = v0.x; raw[1] = v0.y; raw[2] = v1.x; raw[3] = v1.y; raw[4] = v2.x; raw[5] = v2.y;
-        } else {
-            const uint4 v0 = *reinterpret_cast<const uint4 *>(src), v1 = *reinterpret_cast<const uint4 *>(src + 4);
-            raw[0] = v0.x; raw[1] = v0.y; raw[2] = v0.z; raw[3] = v0.w; raw[4] = v1.x; raw[5] = v1.y; raw[6] = v1.z; raw[7] = v1.w;
+    if constexpr (NW == 3) {
+        raw[0] = geo.src[0]; raw[1] = geo.src[1]; raw[2] = geo.src[2];
+    } else if constexpr (NW == 4) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(geo.src);
+        raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w;
+    } else if constexpr (NW == 6) {
+        const uint2 v0 = *reinterpret_cast<const uint2 *>(geo.src), v1 = *reinterpret_cast<const uint2 *>(geo.src + 2),
+                    v2 = *reinterpret_cast<const uint2 *>(geo.src + 4);
+        raw[0] = v0.x; raw[1] = v0.y; raw[2] = v1.x; raw[3] = v1.y; raw[4] = v2.x; raw[5] = v2.y;
+    } else {
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(geo.src), v1 = *reinterpret_cast<const uint4 *>(geo.src + 4);
+        raw[0] = v0.x; raw[1] = v0.y; raw[2] = v0.z; raw[3] = v0.w; raw[4] = v1.x; raw[5] = v1.y; raw[6] = v1.z; raw[7] = v1.w;
+    }
+    // next step consumes row clamp(r+1): advance unless clamped to the first/last row of the band
+    if ((unsigned)(r - p.in_row0) < (unsigned)(p.in_rows - 1)) {
+        geo.src += tp.tile_words;
+        if (++geo.row_in_tile == TR) {
+            geo.k_cur = tma_next_tile(geo.tiles, geo.bars, map, geo.k_cur, geo.tma_x, geo.tma_y0, tp.tile_words, tp.stage_words, lane);
+            geo.row_in_tile = 0;
+            geo.src = geo.tiles + (geo.k_cur % NST) * tp.stage_words + geo.lane_word;
         }
     }
     float f[NPX];
     gray4<CN, BGR>(raw, f);
-    gray4<CN, BGR>(raw + NW / 2, f + 4);
+    if constexpr (NPX == 8) gray4<CN, BGR>(raw + NW / 2, f + 4);
 
     float b[NPX];
     const int yb = BLUR ? r - 2 : r;
@@ -519,12 +573,10 @@ __device__ __forceinline__ void step8(WarpState8<CN> &st, const TmaParams &tp, c
                 for (int j = 0; j < NPX; j++) f[j] = last;
             }
         }
-        geo.slot = geo.slot == 4 ? 0 : geo.slot + 1;
-        {
-            float4 *rp = reinterpret_cast<float4 *>(geo.ring + geo.slot * kRingRow8 + 4 + NPX * lane);
-            rp[0] = make_float4(f[0], f[1], f[2], f[3]);
-            rp[1] = make_float4(f[4], f[5], f[6], f[7]);
-        }
+        geo.ring_cur += kRow;
+        if (geo.ring_cur == geo.ring + 5 * kRow + 4 + NPX * lane) geo.ring_cur -= 5 * kRow;
+#pragma unroll
+        for (int j = 0; j < NPX; j += 4) *reinterpret_cast<float4 *>(geo.ring_cur + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
         float c[NPX + 4];
 #pragma unroll
         for (int j = 0; j < NPX; j++) {
@@ -542,7 +594,7 @@ __device__ __forceinline__ void step8(WarpState8<CN> &st, const TmaParams &tp, c
 #pragma unroll
         for (int j = 0; j < NPX; j++) {
             const float e2 = c[j] + c[j + 4], e1 = c[j + 1] + c[j + 3];
-            const float u = fmaf(p.g2, e2, fmaf(p.g1, e1, fmaf(p.g0, c[j + 2], -0.5f)));
+            const float u = fmaf(p.g2, e2, fmaf(p.g1, e1, fmaf(p.g0, c[j + 2], -0.5f)));  // S~ - 0.5
             const float rr = u + kMagic;
             b[j] = rr - kMagic;
             d[j] = fabsf(u - b[j]);
@@ -554,10 +606,11 @@ __device__ __forceinline__ void step8(WarpState8<CN> &st, const TmaParams &tp, c
             uint32_t mask = 0;
 #pragma unroll
             for (int j = 0; j < NPX; j++) mask |= (d[j] > p.thr ? 1u : 0u) << j;
-            F8 bv;
+            FN<NPX> bv;
 #pragma unroll
             for (int j = 0; j < NPX; j++) bv.v[j] = b[j];
-            bv = blur_exact8(geo.ring, geo.slot, p.w, bv, mask, lane);
+            const int slot = (int)(geo.ring_cur - (geo.ring + 4 + NPX * lane)) / kRow;
+            bv = blur_exact_n<NPX>(geo.ring, slot, p.w, bv, mask, lane);
 #pragma unroll
             for (int j = 0; j < NPX; j++) b[j] = bv.v[j];
             if (p.slow_counter && mask) atomicAdd(p.slow_counter, (unsigned long long)__popc(mask));
@@ -583,17 +636,17 @@ __device__ __forceinline__ void step8(WarpState8<CN> &st, const TmaParams &tp, c
         Dc[j] = e[j + 2] - e[j];
         Sc[j] = fmaf(2.f, e[j + 1], e[j] + e[j + 2]);
     }
-    const int yo = yb - 1;
-    if (__builtin_expect(yo == 0 || yb == H, 0)) {  // BORDER_REFLECT_101 in y
-        if (yo == 0) {
+    if constexpr (SPECIAL) {  // BORDER_REFLECT_101 in y
+        if (yb == 1) {
 #pragma unroll
             for (int j = 0; j < NPX; j++) { st.X0[j] = fmaf(2.f, st.X1[j], Dc[j]); st.S2[j] = Sc[j]; }
-        } else {
+        }
+        if (yb == H) {
 #pragma unroll
             for (int j = 0; j < NPX; j++) { Dc[j] = fmaf(-2.f, st.X1[j], st.X0[j]); Sc[j] = st.S2[j]; }
         }
     }
-    if (yo >= geo.ys) {
+    if constexpr (STORE) {
         uint32_t q[NPX];
 #pragma unroll
         for (int j = 0; j < NPX; j++) {
@@ -603,9 +656,14 @@ __device__ __forceinline__ void step8(WarpState8<CN> &st, const TmaParams &tp, c
             q[j] = __float_as_uint(fminf(m, 255.f) + kMagic);
         }
         const uint32_t lo = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
-        const uint32_t hi = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.v2.u32 [%0], {%1, %2};\n\t}"
-                     ::"l"(geo.dst), "r"(lo), "r"(hi), "r"(geo.store_lane) : "memory");
+        if constexpr (NPX == 8) {
+            const uint32_t hi = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.v2.u32 [%0], {%1, %2};\n\t}"
+                         ::"l"(geo.dst), "r"(lo), "r"(hi), "r"(geo.store_lane) : "memory");
+        } else {
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}"
+                         ::"l"(geo.dst), "r"(lo), "r"(geo.store_lane) : "memory");
+        }
     }
 #pragma unroll
     for (int j = 0; j < NPX; j++) {
@@ -617,30 +675,38 @@ __device__ __forceinline__ void step8(WarpState8<CN> &st, const TmaParams &tp, c
     geo.dst += W;
 }
 
-template <int CN, bool BGR, bool BLUR, bool EDGE>
-__device__ __forceinline__ void run_segment8(WarpState8<CN> &st, const TmaParams &tp, const CUtensorMap *map, Geometry8 &geo, int r,
-                                             int r_last)
+template <int NPX, int CN, bool BGR, bool BLUR, bool EDGE>
+__device__ __forceinline__ void run_segment_t(WarpStateT<NPX> &st, const TmaParams &tp, const CUtensorMap *map, GeometryT &geo, int r,
+                                              int r_last)
 {
+    constexpr int HALO = BLUR ? 3 : 1;
+    const int r_store = geo.ys + HALO;
 #pragma unroll 1
-    for (; r <= r_last; r++) step8<CN, BGR, BLUR, EDGE>(st, tp, map, geo, r);
+    for (; r < r_store; r++) step_t<NPX, CN, BGR, BLUR, EDGE, false, false>(st, tp, map, geo, r);
+    step_t<NPX, CN, BGR, BLUR, EDGE, true, true>(st, tp, map, geo, r);
+    r++;
+#pragma unroll 1
+    for (; r < r_last; r++) step_t<NPX, CN, BGR, BLUR, EDGE, true, false>(st, tp, map, geo, r);
+    if (r == r_last) step_t<NPX, CN, BGR, BLUR, EDGE, true, true>(st, tp, map, geo, r);
 }
 
-template <int CN, bool BGR, bool BLUR>
+template <int NPX, int CN, bool BGR, bool BLUR>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 fused_tma_kernel(const __grid_constant__ TmaParams tp, const __grid_constant__ CUtensorMap map)
 {
     constexpr int HALO = BLUR ? 3 : 1;
+    constexpr int kRow = 32 * NPX + 8;
+    constexpr int kBand = 30 * NPX;
     const FusedParams &p = tp.f;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
-    const int tile_bytes = NST * tp.stage_words * 4;      // multiple of 128
-    Geometry8 geo;
+    const int tile_bytes = NST * tp.stage_words * 4;  // multiple of 128
+    GeometryT geo;
     geo.lane = threadIdx.x & 31;
     geo.tiles = reinterpret_cast<const uint32_t *>(smem + warp * tile_bytes);
-    geo.ring = reinterpret_cast<float *>(smem + kWarpsPerBlock * tile_bytes) + warp * (BLUR ? 5 * kRingRow8 : 0);
-    geo.bars = reinterpret_cast<uint64_t *>(smem + kWarpsPerBlock * tile_bytes + (BLUR ? kWarpsPerBlock * 5 * kRingRow8 * 4 : 0)) + warp * NST;
-    geo.slot = 0;
-    geo.k_cur = -1;
+    geo.ring = reinterpret_cast<float *>(smem + kWarpsPerBlock * tile_bytes) + warp * (BLUR ? 5 * kRow : 0);
+    geo.ring_cur = geo.ring + 4 + NPX * geo.lane;
+    geo.bars = reinterpret_cast<uint64_t *>(smem + kWarpsPerBlock * tile_bytes + (BLUR ? kWarpsPerBlock * 5 * kRow * 4 : 0)) + warp * NST;
 
     int bid = blockIdx.x;
     const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
@@ -650,18 +716,25 @@ fused_tma_kernel(const __grid_constant__ TmaParams tp, const __grid_constant__ C
     if (band >= p.n_bands) return;  // warp-uniform; all synchronisation below is per warp
 
     const int W = p.W;
-    const int x = band * kBandPx8 - NPX + NPX * geo.lane;
+    const int xw = band * kBand - NPX;                // first pixel of lane 0 (a halo lane)
+    const int x = xw + NPX * geo.lane;
     const bool in_img = (x >= 0) && (x < W);
-    geo.lane_last = (W - band * kBandPx8) / NPX;
+    geo.lane_last = (W - band * kBand) / NPX;
     geo.left_edge = (band == 0);
     geo.right_edge = (geo.lane_last <= 31);
     geo.ys = p.out_row0 + seg * p.seg_rows;
     const int ye = min(geo.ys + p.seg_rows, p.out_row0 + p.out_rows);
     geo.store_lane = ((geo.lane >= 1) && (geo.lane <= 30) && in_img) ? 1u : 0u;
     const int r_first = geo.ys - HALO, r_last = ye - 1 + HALO;
-    geo.t0 = min(max(r_first - p.in_row0, 0), p.in_rows - 1);
-    geo.tma_x = ((band * kBandPx8 - tp.box_left_px) * CN) / 4;  // multiple of 4 words; negative / past-the-end columns are zero-filled
-    geo.tma_y0 = frame * p.in_rows + geo.t0;
+    const int t0 = min(max(r_first - p.in_row0, 0), p.in_rows - 1);   // band-relative source row of tile 0
+    // box start: the band start rounded down to a 16-byte boundary of the row (16 px for 3-byte pixels)
+    const int box_px = CN == 3 ? (xw & ~15) : xw;
+    geo.tma_x = (box_px * CN) / 4;
+    geo.lane_word = ((xw - box_px) * CN) / 4 + (NPX * CN / 4) * geo.lane;
+    geo.tma_y0 = frame * p.in_rows + t0;
+    geo.k_cur = 0;
+    geo.row_in_tile = 0;
+    geo.src = geo.tiles + geo.lane_word;
     geo.dst = p.out + (size_t)frame * p.out_rows * W + (ptrdiff_t)(r_first - HALO - p.out_row0) * W + x;
 
     if (geo.lane == 0) {
@@ -674,14 +747,15 @@ fused_tma_kernel(const __grid_constant__ TmaParams tp, const __grid_constant__ C
         }
     }
     __syncwarp();
+    mbar_wait(geo.bars, 0);
 
-    WarpState8<CN> st;
+    WarpStateT<NPX> st;
 #pragma unroll
     for (int j = 0; j < NPX; j++)
         st.a0[j] = st.a1[j] = st.a2[j] = st.a3[j] = st.X0[j] = st.X1[j] = st.S1[j] = st.S2[j] = 0.f;
 
-    if (geo.left_edge || geo.right_edge) run_segment8<CN, BGR, BLUR, true>(st, tp, &map, geo, r_first, r_last);
-    else run_segment8<CN, BGR, BLUR, false>(st, tp, &map, geo, r_first, r_last);
+    if (geo.left_edge || geo.right_edge) run_segment_t<NPX, CN, BGR, BLUR, true>(st, tp, &map, geo, r_first, r_last);
+    else run_segment_t<NPX, CN, BGR, BLUR, false>(st, tp, &map, geo, r_first, r_last);
 
     // drain: TMA loads still in flight target this block's shared memory; wait for them before exit
     for (int kk = geo.k_cur + 1; kk < geo.k_cur + NST; kk++) mbar_wait(geo.bars + (kk % NST), (uint32_t)((kk / NST) & 1));
@@ -808,36 +882,40 @@ static EncodeTiledFn encode_tiled_fn()
 
 static bool tma_usable(int W, int cn, const uint8_t *d_in, const uint8_t *d_out)
 {
-    if (getenv("RIP_FUSED_NO_TMA")) return false;
-    if ((W & 7) || W < 8) return false;                         // 8-pixel lanes
+    // Measured on B200 (profiles/): the TMA-staged variant retires ~13 % more instructions per row
+    // (shared-memory reads + ring bookkeeping) and both variants are issue-bound, so the register /
+    // shuffle kernel with direct global loads is the default.  RIP_FUSED_TMA=1 selects the TMA kernel.
+    const char *want = getenv("RIP_FUSED_TMA");
+    if (!want || atoi(want) == 0) return false;
+    if ((W & 3) || W < 4) return false;                         // 4-pixel lanes
     if (((size_t)W * cn) & 15u) return false;                   // TMA global stride: multiple of 16 bytes
     if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 7u)) return false;
     return encode_tiled_fn() != nullptr;
 }
 
-template <int CN, bool BGR>
+template <int NPX, int CN, bool BGR>
 static cudaError_t launch_tma_t(bool blur, dim3 grid, size_t smem, cudaStream_t s, const TmaParams &tp, const CUtensorMap &map)
 {
-    auto kern = blur ? fused_tma_kernel<CN, BGR, true> : fused_tma_kernel<CN, BGR, false>;
-    static bool attr_done[2] = {false, false};  // per instantiation (static in a template function)
-    if (!attr_done[blur ? 1 : 0] || true) {      // the attribute is per device: set it every time (cheap)
+    auto kern = blur ? fused_tma_kernel<NPX, CN, BGR, true> : fused_tma_kernel<NPX, CN, BGR, false>;
+    if (smem > 48 * 1024) {  // per device and cheap, so set on every launch
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done[blur ? 1 : 0] = true;
     }
     kern<<<grid, kWarpsPerBlock * 32, smem, s>>>(tp, map);
     return cudaSuccess;
 }
 
-static int launch_fused_tma(cudaStream_t s, FusedParams p, int n_frames, int fmt, bool with_blur, int device)
+template <int NPX>
+static int launch_fused_tma_n(cudaStream_t s, FusedParams p, int n_frames, int fmt, bool with_blur, int device)
 {
     const int cn = (fmt == RIP_FMT_RGB8 || fmt == RIP_FMT_BGR8) ? 3 : 4;
+    constexpr int kBand = 30 * NPX, kRow = 32 * NPX + 8;
     TmaParams tp;
-    tp.box_left_px = cn == 3 ? 16 : NPX;
-    tp.tile_words = cn == 3 ? 204 : 256;
-    tp.lane0_word = (tp.box_left_px - NPX) * cn / 4;
+    // RGB: 32*NPX px of lanes + up to 12 px of start rounding, rounded up to 16 px; RGBA: exactly the lanes
+    const int box_px = cn == 3 ? ((32 * NPX + 12 + 15) / 16) * 16 : 32 * NPX;
+    tp.tile_words = box_px * cn / 4;
     tp.stage_words = ((TR * tp.tile_words * 4 + 127) / 128) * 128 / 4;
-    p.n_bands = (p.W + kBandPx8 - 1) / kBandPx8;
+    p.n_bands = (p.W + kBand - 1) / kBand;
     p.n_band_groups = (p.n_bands + kWarpsPerBlock - 1) / kWarpsPerBlock;
     p.seg_rows = pick_seg_rows(p.out_rows, n_frames, p.n_band_groups, device);
     p.n_segs = (p.out_rows + p.seg_rows - 1) / p.seg_rows;
@@ -853,22 +931,29 @@ static int launch_fused_tma(cudaStream_t s, FusedParams p, int n_frames, int fmt
                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(RIP_EINVAL, "rip_fused: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-    const size_t smem = (size_t)kWarpsPerBlock * NST * tp.stage_words * 4 + (with_blur ? (size_t)kWarpsPerBlock * 5 * kRingRow8 * 4 : 0) +
+    const size_t smem = (size_t)kWarpsPerBlock * NST * tp.stage_words * 4 + (with_blur ? (size_t)kWarpsPerBlock * 5 * kRow * 4 : 0) +
                         (size_t)kWarpsPerBlock * NST * 8;
     const long long blocks = (long long)n_frames * p.n_segs * p.n_band_groups;
     if (blocks <= 0 || blocks > 0x7fffffffLL) return fail(RIP_EINVAL, "rip_fused: grid of %lld blocks is out of range", blocks);
     const dim3 grid((unsigned)blocks);
     cudaError_t e = cudaSuccess;
     switch (fmt) {
-    case RIP_FMT_RGB8:  e = launch_tma_t<3, false>(with_blur, grid, smem, s, tp, map); break;
-    case RIP_FMT_BGR8:  e = launch_tma_t<3, true>(with_blur, grid, smem, s, tp, map); break;
-    case RIP_FMT_RGBA8: e = launch_tma_t<4, false>(with_blur, grid, smem, s, tp, map); break;
-    case RIP_FMT_BGRA8: e = launch_tma_t<4, true>(with_blur, grid, smem, s, tp, map); break;
+    case RIP_FMT_RGB8:  e = launch_tma_t<NPX, 3, false>(with_blur, grid, smem, s, tp, map); break;
+    case RIP_FMT_BGR8:  e = launch_tma_t<NPX, 3, true>(with_blur, grid, smem, s, tp, map); break;
+    case RIP_FMT_RGBA8: e = launch_tma_t<NPX, 4, false>(with_blur, grid, smem, s, tp, map); break;
+    case RIP_FMT_BGRA8: e = launch_tma_t<NPX, 4, true>(with_blur, grid, smem, s, tp, map); break;
     default: return fail(RIP_EINVAL, "rip_fused: unsupported input format %d", fmt);
     }
     if (e != cudaSuccess) return cuda_fail(e, "fused_tma_kernel setup", __FILE__, __LINE__);
     RIP_LAUNCH_CHECK();
     return RIP_OK;
+}
+
+static int launch_fused_tma(cudaStream_t s, const FusedParams &p, int n_frames, int fmt, bool with_blur, int device)
+{
+    const char *e = getenv("RIP_FUSED_NPX");
+    if (e && atoi(e) == 8 && (p.W & 7) == 0) return launch_fused_tma_n<8>(s, p, n_frames, fmt, with_blur, device);
+    return launch_fused_tma_n<4>(s, p, n_frames, fmt, with_blur, device);
 }
 
 template <int CN, bool BGR>

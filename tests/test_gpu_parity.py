@@ -134,8 +134,9 @@ def test_sobel_gray_input_matches_opencv_goldens(ctx, golden_cv2_sobel, golden_i
 
 @pytest.mark.parametrize("shape", [(2, 4), (2, 8), (5, 12), (37, 120), (37, 124), (64, 128), (33, 244), (75, 75), (19, 241),
                                    (2, 16), (31, 240), (17, 256), (40, 496)])
-@pytest.mark.parametrize("fmt,cn", [(rip.FMT_RGB8, 3), (rip.FMT_RGBA8, 4), (rip.FMT_BGR8, 3)])
-def test_sobel_colour_input(ctx, oracle, shape, fmt, cn):
+@pytest.mark.parametrize("fmt,cn,tma", [(rip.FMT_RGB8, 3, 0), (rip.FMT_RGBA8, 4, 0), (rip.FMT_BGR8, 3, 0), (rip.FMT_RGB8, 3, 1), (rip.FMT_RGBA8, 4, 1)])
+def test_sobel_colour_input(ctx, oracle, shape, fmt, cn, tma, monkeypatch):
+    monkeypatch.setenv("RIP_FUSED_TMA", str(tma))
     img = synth_frame("uniform", shape[0], shape[1], 21, cn)
     g = oracle.gray(img, oracle.BGR if fmt == rip.FMT_BGR8 else oracle.RGB)
     _eq(ctx.process(img, rip.OP_EDGE, fmt), oracle.sobel(g), f"sobel colour {shape} cn={cn}")
@@ -160,8 +161,9 @@ FUSED_SHAPES = [(2, 4), (3, 8), (7, 12), (16, 120), (40, 124), (9, 128), (70, 24
 
 
 @pytest.mark.parametrize("shape", FUSED_SHAPES)
-@pytest.mark.parametrize("kind", ["uniform", "smooth"])
-def test_fused_single_kernel_path(ctx, oracle, shape, kind):
+@pytest.mark.parametrize("kind,tma", [("uniform", 0), ("smooth", 0), ("uniform", 1)])
+def test_fused_single_kernel_path(ctx, oracle, shape, kind, tma, monkeypatch):
+    monkeypatch.setenv("RIP_FUSED_TMA", str(tma))  # 1: TMA-staged kernel where the shape allows it
     img = synth_frame(kind, shape[0], shape[1], 31)
     w = rip.gauss_weights(5, 1.0)
     _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w, threads=0),
@@ -169,8 +171,9 @@ def test_fused_single_kernel_path(ctx, oracle, shape, kind):
 
 
 @pytest.mark.parametrize("fmt,cn,order", [(rip.FMT_RGBA8, 4, "RGB"), (rip.FMT_BGR8, 3, "BGR"), (rip.FMT_BGRA8, 4, "BGR")])
-@pytest.mark.parametrize("sigma", [1.0, 1.5])
-def test_fused_formats_and_sigmas(ctx, oracle, fmt, cn, order, sigma):
+@pytest.mark.parametrize("sigma,tma", [(1.0, 0), (1.5, 0), (1.5, 1)])
+def test_fused_formats_and_sigmas(ctx, oracle, fmt, cn, order, sigma, tma, monkeypatch):
+    monkeypatch.setenv("RIP_FUSED_TMA", str(tma))
     img = synth_frame("smooth", 97, 248, 41, cn)
     w = rip.gauss_weights(5, sigma)
     want = oracle.fused(img, 5, weights=w, order=oracle.BGR if order == "BGR" else oracle.RGB)
@@ -225,9 +228,8 @@ def test_fused_ldg_and_tma_kernels_agree(oracle, monkeypatch):
     d_in = rip.DeviceBuffer(img.nbytes).upload(img)
     d_out = rip.DeviceBuffer(h * wd)
     outs = []
-    for no_tma in (False, True):
-        if no_tma:
-            monkeypatch.setenv("RIP_FUSED_NO_TMA", "1")
+    for use_tma in (True, False):
+        monkeypatch.setenv("RIP_FUSED_TMA", "1" if use_tma else "0")
         rip.lib().rip_memset_device_async(0, d_out.ptr, 0, h * wd, None)
         rip.fused_dev(d_in.ptr, d_out.ptr, wd, h, 1, rip.FMT_RGB8, 5, w)
         outs.append(d_out.download((h, wd)))
@@ -249,8 +251,9 @@ def test_fused_guard_band_statistics():
         assert lo <= frac <= hi, (kind, frac)
 
 
-@pytest.mark.parametrize("wd", [360, 368])  # LDG kernel / TMA kernel
-def test_fused_row_bands_equal_whole_frame(ctx, oracle, wd):
+@pytest.mark.parametrize("wd,tma", [(360, 0), (368, 0), (368, 1)])  # LDG kernel / TMA kernel
+def test_fused_row_bands_equal_whole_frame(ctx, oracle, wd, tma, monkeypatch):
+    monkeypatch.setenv("RIP_FUSED_TMA", str(tma))
     h = 200
     img = synth_frame("uniform", h, wd, 81)
     w = rip.gauss_weights(5, 1.0)
