@@ -77,7 +77,8 @@ def build_host(force: bool = False, verbose: bool = False) -> str | None:
         glob.glob(os.path.join(INCLUDE, "*.h"))
     if force or _stale(LIB_HOST, deps) or _stale(LIB_HOST, [LIB_CUDA]):
         cmd = [_host_cxx(), "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-pthread",
-               "-I", INCLUDE, "-I", HOST, "-o", LIB_HOST, *srcs,
+               "-I", INCLUDE, "-I", HOST, "-I", os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "include"),
+               "-o", LIB_HOST, *srcs,
                "-L", PKG, "-lrip_cuda", "-Wl,-rpath,$ORIGIN"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or res.returncode:

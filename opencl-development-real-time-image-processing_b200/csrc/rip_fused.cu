@@ -38,6 +38,19 @@
 #ifndef RIP_LDG_MINBLOCKS
 #define RIP_LDG_MINBLOCKS 6
 #endif
+// x2 kernel (rip_fused_x2.cuh): prefetch depth in rows, resident blocks per SM, row-loop unroll
+#ifndef RIP_X2_PF
+#define RIP_X2_PF 2
+#endif
+#ifndef RIP_X2_MINB8
+#define RIP_X2_MINB8 4
+#endif
+#ifndef RIP_X2_MINB4
+#define RIP_X2_MINB4 6
+#endif
+#ifndef RIP_X2_UNROLL
+#define RIP_X2_UNROLL 3
+#endif
 
 namespace rip {
 
@@ -138,6 +151,8 @@ __device__ __forceinline__ RawRow<CN> load_row(const uint8_t *p, bool valid)
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kRingRow = 128 + 8;  // floats per gray row in the per-warp shared ring (4 pad each side)
+
+#include "rip_fused_x2.cuh"
 
 // Per-warp sliding-window state, all in registers.  The row loop is NOT unrolled: the whole hot
 // loop is ~3 KB of SASS and stays resident in the per-partition instruction cache (an earlier
@@ -782,7 +797,7 @@ bool fused_supported(int W, int H, int fmt, int ksize, const uint8_t *d_in, cons
 // ("Exact blur at separable cost") for the derivation:
 //   |S_ref - S| <= u * 255 * (sum_i w_i (25 - i) + sum_i w_i)      (sequential fp32 sum, u = 2^-24)
 //   |S~    - S| <= 255 * sum|w_ij - g_i g_j|  +  9 u * 255 * sum_i w_i   (separable FMA evaluation)  The kernel compares |frac(S~) - 0.5| against 0.5 - band.
-bool fused_plan_weights(const float *w25, float g[3], float *thr)
+static bool plan_weights_band(const float *w25, float g[3], double *band_out)
 {
     double sum = 0.0;
     for (int i = 0; i < 25; i++) {
@@ -806,11 +821,19 @@ bool fused_plan_weights(const float *w25, float g[3], float *thr)
     for (int i = 0; i < 25; i++) cum += (double)w25[i] * (25 - i);
     const double band = 255.0 * dev + u * 255.0 * (cum + sum + 9.0 * sum) * 1.02 + 1e-6;
     if (band > 0.05) return false;  // weights are not (close to) a symmetric separable kernel
+    *band_out = band;
+    return true;
+}
+
+bool fused_plan_weights(const float *w25, float g[3], float *thr)
+{
+    double band;
+    if (!plan_weights_band(w25, g, &band)) return false;
     *thr = (float)(0.5 - band);
     return true;
 }
 
-static int pick_seg_rows(int out_rows, int n_frames, int n_band_groups, int device)
+static int pick_seg_rows(int out_rows, int n_frames, int n_band_groups, int device, int resident_blocks = 6)
 {
     if (const char *e = getenv("RIP_FUSED_SEG")) {
         const int v = atoi(e);
@@ -818,7 +841,7 @@ static int pick_seg_rows(int out_rows, int n_frames, int n_band_groups, int devi
     }
     // enough blocks for >= ~8 waves of (SMs x 6 resident blocks), but segments of >= 64 rows so the
     // 6 warm-up rows stay below 10 %; never more than 256 rows (tail balance).
-    const long long target_blocks = (long long)sm_count(device) * 6 * 8;
+    const long long target_blocks = (long long)sm_count(device) * resident_blocks * 8;
     int seg = 256;
     while (seg > 64 && (long long)n_frames * n_band_groups * ((out_rows + seg - 1) / seg) < target_blocks) seg >>= 1;
     if (seg > out_rows) seg = out_rows;
@@ -956,6 +979,66 @@ static int launch_fused_tma(cudaStream_t s, const FusedParams &p, int n_frames, 
     return launch_fused_tma_n<4>(s, p, n_frames, fmt, with_blur, device);
 }
 
+// ---- x2 kernel (the default) --------------------------------------------------------------------
+template <int NPX, int CN, bool BGR>
+static void launch_x2_t(bool blur, dim3 grid, cudaStream_t s, const X2Params &xp)
+{
+    if (blur) fused_x2_kernel<NPX, CN, BGR, true><<<grid, kWarpsPerBlock * 32, 0, s>>>(xp);
+    else fused_x2_kernel<NPX, CN, BGR, false><<<grid, kWarpsPerBlock * 32, 0, s>>>(xp);
+}
+
+template <int NPX>
+static int launch_fused_x2_n(cudaStream_t s, FusedParams p, int n_frames, int fmt, bool with_blur, double band, const float g[3], int device)
+{
+    constexpr int kBand = 30 * NPX;
+    X2Params xp;
+    memset(&xp, 0, sizeof(xp));
+    p.n_bands = (p.W + kBand - 1) / kBand;
+    p.n_band_groups = (p.n_bands + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    p.seg_rows = pick_seg_rows(p.out_rows, n_frames, p.n_band_groups, device, NPX == 8 ? RIP_X2_MINB8 : RIP_X2_MINB4);
+    p.n_segs = (p.out_rows + p.seg_rows - 1) / p.seg_rows;
+    xp.f = p;
+    if (with_blur) {
+        // gray enters the vertical pass as an integer bit pattern (value q * 2^-149): the vertical
+        // taps carry 2^75 and the horizontal taps 2^74 (powers of two: every rounding is unchanged)
+        xp.gv0 = std::ldexp(g[0], 75); xp.gv1 = std::ldexp(g[1], 75); xp.gv2 = std::ldexp(g[2], 75);
+        xp.gh0 = std::ldexp(g[0], 74); xp.gh1 = std::ldexp(g[1], 74); xp.gh2 = std::ldexp(g[2], 74);
+        // S~ + 256 is rounded to a multiple of ulp = 2^-15 (error <= ulp/2).  A pixel whose 15 fraction
+        // bits are >= a and <= 2^15 - 1 - a has frac(S~) in [(a - 1/2) ulp, 1 - (a + 1/2) ulp], i.e. S~ is
+        // >= band away from an integer when a >= band / ulp + 1/2; all others are replayed exactly.
+        const double ulp = std::ldexp(1.0, -kFracBits);
+        const uint32_t a = (uint32_t)std::ceil(band / ulp + 0.5);
+        xp.zoff = a << (32 - kFracBits);
+        xp.zthr = (2u * a) << (32 - kFracBits);
+    }
+    const long long blocks = (long long)n_frames * p.n_segs * p.n_band_groups;
+    if (blocks <= 0 || blocks > 0x7fffffffLL) return fail(RIP_EINVAL, "rip_fused: grid of %lld blocks is out of range", blocks);
+    const dim3 grid((unsigned)blocks);
+    switch (fmt) {
+    case RIP_FMT_RGB8:  launch_x2_t<NPX, 3, false>(with_blur, grid, s, xp); break;
+    case RIP_FMT_BGR8:  launch_x2_t<NPX, 3, true>(with_blur, grid, s, xp); break;
+    case RIP_FMT_RGBA8: launch_x2_t<NPX, 4, false>(with_blur, grid, s, xp); break;
+    case RIP_FMT_BGRA8: launch_x2_t<NPX, 4, true>(with_blur, grid, s, xp); break;
+    default: return fail(RIP_EINVAL, "rip_fused: unsupported input format %d", fmt);
+    }
+    RIP_LAUNCH_CHECK();
+    return RIP_OK;
+}
+
+// which kernel runs: RIP_FUSED_KERNEL = x2 (default) | ldg | tma; RIP_FUSED_NPX = 8 | 4 pixels per lane
+static int x2_npx(int W, int cn, const uint8_t *d_in, const uint8_t *d_out)
+{
+    const char *k = getenv("RIP_FUSED_KERNEL");
+    if (k && strcmp(k, "x2") != 0) return 0;
+    if (getenv("RIP_FUSED_TMA") && atoi(getenv("RIP_FUSED_TMA")) != 0) return 0;
+    int want = 8;
+    if (const char *e = getenv("RIP_FUSED_NPX")) want = atoi(e) == 4 ? 4 : 8;
+    const uintptr_t in_align8 = cn == 4 ? 15u : 7u;
+    const bool ok8 = (W & 7) == 0 && !(reinterpret_cast<uintptr_t>(d_in) & in_align8) && !(reinterpret_cast<uintptr_t>(d_out) & 7u);
+    if (want == 8 && ok8) return 8;
+    return 4;  // fused_supported() already guarantees W % 4 == 0 and the 4-pixel alignments
+}
+
 template <int CN, bool BGR>
 static void launch_t(bool blur, dim3 grid, cudaStream_t s, const FusedParams &p)
 {
@@ -977,15 +1060,20 @@ int launch_fused(cudaStream_t s, const uint8_t *d_in, uint8_t *d_out, int W, int
     p.seg_rows = pick_seg_rows(out_rows, n_frames, p.n_band_groups, device);
     p.n_segs = (out_rows + p.seg_rows - 1) / p.seg_rows;
     p.slow_counter = g_slow_counter;
+    double band = 0.0;
+    float g[3] = {0.f, 0.f, 0.f};
     if (with_blur) {
-        float g[3];
-        if (!fused_plan_weights(weights25, g, &p.thr))
+        if (!plan_weights_band(weights25, g, &band))
             return fail(RIP_EUNSUPPORTED, "rip_fused: weights are not a non-negative symmetric separable 5x5 kernel");
+        p.thr = (float)(0.5 - band);
         p.g0 = g[0]; p.g1 = g[1]; p.g2 = g[2];
         memcpy(p.w, weights25, sizeof(float) * 25);
     }
     {
         const int cn = (fmt == RIP_FMT_RGB8 || fmt == RIP_FMT_BGR8) ? 3 : 4;
+        const int npx = x2_npx(W, cn, d_in, d_out);
+        if (npx == 8) return launch_fused_x2_n<8>(s, p, n_frames, fmt, with_blur, band, g, device);
+        if (npx == 4) return launch_fused_x2_n<4>(s, p, n_frames, fmt, with_blur, band, g, device);
         if (tma_usable(W, cn, d_in, d_out)) return launch_fused_tma(s, p, n_frames, fmt, with_blur, device);
     }
     const long long blocks = (long long)n_frames * p.n_segs * p.n_band_groups;
@@ -1052,6 +1140,53 @@ __global__ void selftest_gray_kernel(unsigned long long *bad)
     }
 }
 
+// the x2 kernel's versions of the same two shortcuts: (1) sqrt.approx, then a multiply by 2^-149 (or
+// 2^-127 on the 2^-22-scaled values of the no-blur variant) whose denormal result IS the rounded
+// integer, then I2IP.U8.S32.SAT; (2) IDP.2A + FMUL2.RM / FFMA2.RP gray with the cold (r,g) lookup.
+__global__ void selftest_sqrt_x2_kernel(unsigned long long *bad)
+{
+    const unsigned m2_max = 2u * 1020u * 1020u;
+    const float s44 = __uint_as_float((127u - 44u) << 23);  // 2^-44
+    for (unsigned m2 = blockIdx.x * blockDim.x + threadIdx.x; m2 <= m2_max; m2 += gridDim.x * blockDim.x) {
+        const unsigned want = (unsigned)min(__float2int_rn(__fsqrt_rn((float)m2)), 255);
+        const u64 a = mul2(pk2(sqrt_approx((float)m2), sqrt_approx((float)m2 * s44)),
+                           pk2(__uint_as_float(1u), __uint_as_float(0x00400000u)));
+        const uint32_t packed = i2ip(hi2u(a), lo2u(a), 0u);
+        if ((packed & 0xffu) != want || ((packed >> 8) & 0xffu) != want) atomicAdd(bad, 1ull);
+    }
+}
+
+template <int NPX, int CN, bool BGR>
+__global__ void selftest_gray_x2_kernel(unsigned long long *bad)
+{
+    constexpr int NP = NPX / 2, NW = NPX * CN / 4;
+    // thread q handles triples NPX*q .. NPX*q + NPX-1 (triple i: c0 = i & 255, c1 = (i >> 8) & 255, c2 = i >> 16)
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < (1u << 24) / NPX; q += gridDim.x * blockDim.x) {
+        uint8_t bytes[NW * 4];
+#pragma unroll
+        for (int j = 0; j < NPX; j++) {
+            const unsigned i = NPX * q + j;
+            bytes[CN * j + 0] = i & 255u; bytes[CN * j + 1] = (i >> 8) & 255u; bytes[CN * j + 2] = i >> 16;
+            if (CN == 4) bytes[4 * j + 3] = (uint8_t)(i * 37u);  // alpha must be ignored
+        }
+        uint32_t w[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++)
+            w[k] = bytes[4 * k] | (bytes[4 * k + 1] << 8) | (bytes[4 * k + 2] << 16) | ((uint32_t)bytes[4 * k + 3] << 24);
+        u64 Q[NP], E[NP];
+        const uint32_t any = gray_x2<NPX, CN, BGR>(w, Q, E);
+        if (any & 1u) gray_fix_x2<NPX, CN, BGR>(w, Q, E);
+#pragma unroll
+        for (int j = 0; j < NPX; j++) {
+            const unsigned i = NPX * q + j;
+            const unsigned c0 = i & 255u, c1 = (i >> 8) & 255u, c2 = i >> 16;
+            const unsigned want = BGR ? gray_exact(c2, c1, c0) : gray_exact(c0, c1, c2);
+            const unsigned got = j < NP ? lo2u(Q[j % NP]) : hi2u(Q[j % NP]);
+            if (got != want) atomicAdd(bad, 1ull);
+        }
+    }
+}
+
 }  // namespace
 
 int fused_selftest(int device, unsigned long long *checked, unsigned long long *mismatches)
@@ -1066,14 +1201,23 @@ int fused_selftest(int device, unsigned long long *checked, unsigned long long *
     selftest_gray_kernel<3, true><<<grid, 256>>>(d_bad);
     selftest_gray_kernel<4, false><<<grid, 256>>>(d_bad);
     selftest_gray_kernel<4, true><<<grid, 256>>>(d_bad);
+    selftest_sqrt_x2_kernel<<<grid, 256>>>(d_bad);
+    selftest_gray_x2_kernel<8, 3, false><<<grid, 256>>>(d_bad);
+    selftest_gray_x2_kernel<8, 3, true><<<grid, 256>>>(d_bad);
+    selftest_gray_x2_kernel<8, 4, false><<<grid, 256>>>(d_bad);
+    selftest_gray_x2_kernel<8, 4, true><<<grid, 256>>>(d_bad);
+    selftest_gray_x2_kernel<4, 3, false><<<grid, 256>>>(d_bad);
+    selftest_gray_x2_kernel<4, 3, true><<<grid, 256>>>(d_bad);
+    selftest_gray_x2_kernel<4, 4, false><<<grid, 256>>>(d_bad);
+    selftest_gray_x2_kernel<4, 4, true><<<grid, 256>>>(d_bad);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     unsigned long long bad = 0;
     if (e == cudaSuccess) e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
     cudaFree(d_bad);
     if (e != cudaSuccess) return cuda_fail(e, "fused_selftest", __FILE__, __LINE__);
-    count_launch(5);
-    *checked = (2ull * 1020ull * 1020ull + 1ull) + 4ull * (1ull << 24);
+    count_launch(14);
+    *checked = 3ull * (2ull * 1020ull * 1020ull + 1ull) + 12ull * (1ull << 24);
     *mismatches = bad;
     return RIP_OK;
 }

@@ -1,0 +1,474 @@
+// rip_fused_x2.cuh -- the production fused kernel: gray -> 5x5 Gaussian -> 3x3 Sobel (or gray -> Sobel) in
+// one pass, written around what tools/pipe_probe.cu measured on B200 (profiles/pipe_probe_r1.txt):
+//
+//   pipe          lanes/clk/SM   used here for
+//   FMA  (fp32)   128            FFMA2/FADD2/FMUL2 (two pixels per instruction: half the issue slots,
+//                                same pipe time), IDP.2A (64/clk)
+//   ALU           64             LOP3, VIMNMX3, I2IP, LEA (LEA measured at 128/clk)
+//   XU            16             MUFU.SQRT only (I2F/F2I/FRND and IMAD.WIDE/.HI are slow: none are used)
+//   LSU/shuffle   32             LDG, SHFL, STS, STG
+//
+// The kernel is FMA-pipe bound (~26 fp32 lane-operations per pixel), so everything that is not a
+// multiply-add was moved off that pipe or removed:
+//   * gray: t = 299r+587g+114b by IDP.2A; the INTEGER bit pattern of t, read as a float, is the
+//     denormal t*2^-149, so floor(t/1000) is ONE multiply rounded toward -inf by the float just above
+//     1/1000 (FMUL2.RM), and its result is again an integer bit pattern that feeds the blur's FFMAs
+//     directly (denormal operands run at full rate; the taps carry the 2^149 back).  No IMAD.WIDE,
+//     no I2F.  A second FMA rounded toward +inf with the float just below 1/1000 yields 1 exactly
+//     on the multiples of 1000, the only triples where the reference's double arithmetic
+//     (Comparator.cpp:41) can land one below t/1000 (looked up per (r,g), cold path).
+//   * blur: separable fp32 fast path; S~ + 256 puts floor(S~) in mantissa bits 15..22 and the
+//     fraction in bits 0..14, so the guard band test is one LEA + VIMNMX3 per pixel and the rounded
+//     value 256+b one LOP3 -- no float subtractions.  Pixels inside the guard band are replayed
+//     with the reference's exact 25-tap sequence (GaussianBlur.cpp:236-258) from a shared-memory ring.
+//   * Sobel runs on the biased values 256+b (all sums stay exact in fp32), the magnitude's
+//     round-half-even + saturation is an FMUL2 by 2^-149 (the result's bit pattern IS the integer)
+//     followed by I2IP.U8.S32.SAT, which also packs the bytes.
+//   * a lane owns NPX horizontally adjacent pixels, pixel j paired with pixel j+NPX/2 in one 64-bit
+//     register so that every horizontal tap of a pair is again an aligned pair; the row loop is
+//     unrolled by 3 over three input-row buffers (loads run three rows ahead), so the buffer rotation
+//     and the two-row Sobel delay line are register renames, not moves.
+//
+// Included by rip_fused.cu inside its anonymous namespace (shares FusedParams, the gray table and the
+// exact replay conventions with the older kernels kept there for A/B runs).
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ u64 pk2u(uint32_t lo, uint32_t hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ float lo2(u64 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float hi2(u64 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ uint32_t lo2u(u64 v) { return (uint32_t)v; }
+__device__ __forceinline__ uint32_t hi2u(u64 v) { return (uint32_t)(v >> 32); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2_rm(u64 a, u64 b) { u64 d; asm("mul.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fma2_rp(u64 a, u64 b, u64 c) { u64 d; asm("fma.rp.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// d = (c & 0xffff) << 16 | sat_u8(a) << 8 | sat_u8(b)
+__device__ __forceinline__ uint32_t i2ip(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+constexpr float kInvK_up = 1.0000000474974513e-3f;   // 0x3A83126F: the float just ABOVE 1/1000
+constexpr float kInvK_dn = 9.9999993108212948e-4f;   // 0x3A83126E: the float just BELOW 1/1000
+constexpr float kBias = 256.0f;                      // [256, 512): ulp 2^-15, floor(S~) in mantissa bits 15..22
+constexpr uint32_t kBiasMask = 0xffff8000u;
+constexpr int kFracBits = 15;
+
+struct X2Params {
+    FusedParams f;
+    float gv0, gv1, gv2;   // vertical taps   * 2^75  (gray enters as the integer bit pattern q = q * 2^-149)
+    float gh0, gh1, gh2;   // horizontal taps * 2^74
+    uint32_t zoff, zthr;   // guard band: pixel is replayed iff ((bits << 19) + zoff) < zthr  (unsigned, mod 2^32)
+};
+
+// ---- exact gray of NPX packed pixels -> NPX/2 pairs of integer bit patterns ---------------------
+// returns the OR of the "t is a multiple of 1000" flags in bit 0
+template <int NPX, int CN, bool BGR>
+__device__ __forceinline__ uint32_t gray_x2(const uint32_t *w, u64 *Q, u64 *E)
+{
+    constexpr int NP = NPX / 2;
+    constexpr uint32_t cA = BGR ? 114u : 299u, cB = 587u, cC = BGR ? 299u : 114u;  // weights of byte 0,1,2
+    constexpr uint32_t AB = cA | (cB << 16), C0 = cC, zA = cA << 16, BC = cB | (cC << 16);
+    uint32_t t[NPX];
+#pragma unroll
+    for (int g = 0; g < NPX / 4; g++) {
+        const uint32_t *v = w + g * CN;
+        if constexpr (CN == 4) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) t[4 * g + j] = __dp2a_hi(C0, v[j], __dp2a_lo(AB, v[j], 0u));  // alpha x 0
+        } else {
+            // byte stream: p0 = v0.b0-2, p1 = v0.b3 v1.b0-1, p2 = v1.b2-3 v2.b0, p3 = v2.b1-3
+            t[4 * g + 0] = __dp2a_hi(C0, v[0], __dp2a_lo(AB, v[0], 0u));
+            t[4 * g + 1] = __dp2a_lo(BC, v[1], __dp2a_hi(zA, v[0], 0u));
+            t[4 * g + 2] = __dp2a_lo(C0, v[2], __dp2a_hi(AB, v[1], 0u));
+            t[4 * g + 3] = __dp2a_hi(BC, v[2], __dp2a_lo(zA, v[2], 0u));
+        }
+    }
+    const u64 up = pk2(kInvK_up, kInvK_up), ndn = pk2(-kInvK_dn, -kInvK_dn);
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        const u64 T = pk2u(t[j], t[j + NP]);
+        Q[j] = mul2_rm(T, up);        // floor(t * up) = floor(t / 1000)          (t <= 255000)
+        E[j] = fma2_rp(T, ndn, Q[j]); // ceil(q - t * dn): 1 iff t = 1000 q > 0, else -0 / +0
+        any |= lo2u(E[j]) | hi2u(E[j]);
+    }
+    return any;
+}
+
+// Cold, out of line: for the pixels flagged in `m` (t is a multiple of 1000) look up the (r,g)-indexed bit
+// that says whether the reference's double evaluation lands one below t/1000.  Scalar arguments only
+// (they travel in registers); returns the mask of pixels whose gray must be decremented.
+template <int CN, bool BGR>
+__device__ __noinline__ uint32_t gray_down_mask(uint32_t m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+                                                uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7)
+{
+    uint32_t out = 0;
+    while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const int off = CN * j, wi = off >> 2;
+        const uint32_t lo = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : wi == 3 ? w3 : wi == 4 ? w4 : wi == 5 ? w5 : wi == 6 ? w6 : w7;
+        const uint32_t hi = wi == 0 ? w1 : wi == 1 ? w2 : wi == 2 ? w3 : wi == 3 ? w4 : wi == 4 ? w5 : wi == 5 ? w6 : w7;
+        const uint32_t px = __byte_perm(lo, hi, 0x3210u + 0x1111u * (uint32_t)(off & 3));  // channel bytes in bits 0..23
+        const uint32_t r = BGR ? (px >> 16) & 0xffu : px & 0xffu, g = (px >> 8) & 0xffu;
+        const uint32_t idx = (r << 8) | g;
+        out |= ((__ldg(&d_gray_down[idx >> 5]) >> (idx & 31u)) & 1u) << j;
+    }
+    return out;
+}
+
+template <int NPX, int CN, bool BGR>
+__device__ __forceinline__ void gray_fix_x2(const uint32_t *w, u64 *Q, const u64 *E)
+{
+    constexpr int NP = NPX / 2, NW = NPX * CN / 4;
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < NP; j++) m |= ((lo2u(E[j]) & 1u) << j) | ((hi2u(E[j]) & 1u) << (j + NP));
+    const uint32_t d = gray_down_mask<CN, BGR>(m, w[0], w[1], w[2], NW > 3 ? w[NW > 3 ? 3 : 0] : 0u, NW > 4 ? w[NW > 4 ? 4 : 0] : 0u,
+                                               NW > 5 ? w[NW > 5 ? 5 : 0] : 0u, NW > 6 ? w[NW > 6 ? 6 : 0] : 0u, NW > 7 ? w[NW > 7 ? 7 : 0] : 0u);
+#pragma unroll
+    for (int j = 0; j < NP; j++) Q[j] = pk2u(lo2u(Q[j]) - ((d >> j) & 1u), hi2u(Q[j]) - ((d >> (j + NP)) & 1u));
+}
+
+template <int NPX, int CN>
+struct RawX {
+    uint32_t w[NPX * CN / 4];
+};
+
+// Unpredicated: lanes outside the image read the start of the row (their pointer has x offset 0) and
+// their pixels are never consumed.  A predicated load would tie each destination register to its
+// previous value and turn the rotation of the prefetch registers into moves.
+template <int NPX, int CN>
+__device__ __forceinline__ void load_row_x2(RawX<NPX, CN> &r, const uint8_t *p)
+{
+    constexpr int NW = NPX * CN / 4;
+    if constexpr (NW == 3) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+        r.w[0] = __ldg(q); r.w[1] = __ldg(q + 1); r.w[2] = __ldg(q + 2);
+    } else if constexpr (NW == 4) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+        r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+    } else if constexpr (NW == 6) {
+        const uint2 *q = reinterpret_cast<const uint2 *>(p);
+        const uint2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+        r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y; r.w[4] = c.x; r.w[5] = c.y;
+    } else {
+        const uint4 *q = reinterpret_cast<const uint4 *>(p);
+        const uint4 a = __ldg(q), b = __ldg(q + 1);
+        r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w; r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+    }
+}
+
+template <int NPX, int CN>
+struct WarpX {
+    u64 a0[NPX / 2], a1[NPX / 2], a2[NPX / 2], a3[NPX / 2];  // pending vertical sums of blurred rows r-2 .. r+1
+    u64 F1[NPX / 2], F2[NPX / 2];                            // rows yb-1 and yb-2 of the image the Sobel stage reads
+};
+
+struct GeoX {
+    const uint8_t *src;      // this lane's pixels in the input row that was loaded last
+    uint8_t *dst;            // this lane's pixels in the output row produced next
+    uint32_t ring_warp;      // shared-memory byte address of this warp's gray ring [5][32*NPX] (integer gray;
+                             // within a lane's NPX words the pixels sit in register order: pairs (j, j+NPX/2))
+    uint32_t ring_cur;       // byte address of this lane's words in the ring row holding the newest gray row
+    uint32_t w25;            // shared-memory byte address of the exact 2-D weights (for the replay)
+    uint32_t in_pitch;
+    int adv_lo, adv_n;       // the source pointer advances before the load of step r iff 0 <= r - adv_lo < adv_n
+    int lane, lane_last;
+    bool left_edge, right_edge;
+    uint32_t store_lane;
+    int r_store, r_last;     // first / last step that produces an output row
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+
+// Cold, out of line: the reference's 25-tap sum (GaussianBlur.cpp:236-258) for ONE pixel, column `c`
+// of the warp's band (0 = pixel 0 of lane 0): ky-major / kx-minor from 0.0f, unfused multiply and
+// add, clamp, truncate.  Returns the biased value kBias + b.  Columns outside the band are clamped:
+// they only feed blurred values of the halo lanes that no stored output consumes.
+template <int NPX>
+__device__ __noinline__ float blur_exact_one(uint32_t ring_warp, int c, int slot_new, uint32_t w25)
+{
+    constexpr int NP = NPX / 2;
+    uint32_t col[5];
+#pragma unroll
+    for (int kx = 0; kx < 5; kx++) {
+        const int cc = min(max(c + kx - 2, 0), 32 * NPX - 1);
+        const int k = cc % NPX;
+        col[kx] = ring_warp + 4u * (uint32_t)((cc - k) + 2 * (k % NP) + k / NP);
+    }
+    float acc = 0.f;
+    int slot = slot_new;
+#pragma unroll
+    for (int ky = 0; ky < 5; ky++) {
+        slot = slot == 4 ? 0 : slot + 1;  // oldest row first
+        const uint32_t row = (uint32_t)slot * (32 * NPX * 4);
+#pragma unroll
+        for (int kx = 0; kx < 5; kx++) acc = __fadd_rn(acc, __fmul_rn((float)lds_u32(col[kx] + row), lds_f32(w25 + 4 * (ky * 5 + kx))));
+    }
+    return kBias + truncf(fminf(fmaxf(acc, 0.f), 255.f));
+}
+
+// One image row of the sliding window: consumes the input row held in `buf` (row r, clamped to the
+// rows of the band), refills `buf` with row r + 3, and -- for kRstore <= r <= r_last -- stores output
+// row r - HALO.  The border rules are applied at run time (a few uniform branches per row), so this is
+// the only copy of the row body; the caller unrolls it by three with three row buffers, which makes
+// the buffer rotation and the two-row Sobel delay line pure register renames.
+template <int NPX, int CN, bool BGR, bool BLUR>
+__device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, const X2Params &xp, GeoX &geo, int r)
+{
+    constexpr int NP = NPX / 2;
+    constexpr int kRowB = 32 * NPX * 4;  // bytes per ring row
+    const FusedParams &p = xp.f;
+    const int W = p.W, H = p.H, lane = geo.lane;
+    const bool edge = geo.left_edge || geo.right_edge;
+
+    // ---- 1. gray of row r; refill the buffer with row r + 3 ---------------------------------------
+    u64 Q[NP];
+    {
+        u64 E[NP];
+        const uint32_t any = gray_x2<NPX, CN, BGR>(buf.w, Q, E);
+        if (__builtin_expect(__any_sync(FULL, any & 1u), 0)) gray_fix_x2<NPX, CN, BGR>(buf.w, Q, E);
+        if ((unsigned)(r - geo.adv_lo) < (unsigned)geo.adv_n) geo.src += geo.in_pitch;
+        load_row_x2<NPX, CN>(buf, geo.src);
+    }
+
+    // F[j] = (f[j], f[j + NP]): the row the Sobel stage consumes (blurred row yb, biased by kBias, or
+    // the gray row scaled to normal floats when there is no blur stage)
+    u64 F[NP];
+    const int yb = BLUR ? r - 2 : r;
+    if constexpr (BLUR) {
+        if (edge) {  // clamp-to-edge columns (GaussianBlur.cpp:240)
+            const uint32_t first = __shfl_sync(FULL, lo2u(Q[0]), 1);
+            const uint32_t last = __shfl_sync(FULL, hi2u(Q[NP - 1]), min(geo.lane_last, 31));
+            if (geo.left_edge && lane == 0) {
+#pragma unroll
+                for (int j = 0; j < NP; j++) Q[j] = pk2u(first, first);
+            }
+            if (geo.right_edge && lane > geo.lane_last) {
+#pragma unroll
+                for (int j = 0; j < NP; j++) Q[j] = pk2u(last, last);
+            }
+        }
+        // park the integer gray row in the shared ring (only the cold exact replay reads it back)
+        geo.ring_cur += kRowB;
+        if (geo.ring_cur >= geo.ring_warp + 5 * kRowB) geo.ring_cur -= 5 * kRowB;
+#pragma unroll
+        for (int j = 0; j < NP; j += 2)
+            asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(geo.ring_cur + 8 * j), "l"(Q[j]), "l"(Q[j + 1]) : "memory");
+        // vertical pass, accumulate form: row r completes blurred row r-2
+        const u64 GV0 = pk2(xp.gv0, xp.gv0), GV1 = pk2(xp.gv1, xp.gv1), GV2 = pk2(xp.gv2, xp.gv2);
+        u64 V[NP];
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            V[j] = fma2(GV2, Q[j], st.a0[j]);
+            st.a0[j] = fma2(GV1, Q[j], st.a1[j]);
+            st.a1[j] = fma2(GV0, Q[j], st.a2[j]);
+            st.a2[j] = fma2(GV1, Q[j], st.a3[j]);
+            st.a3[j] = mul2(GV2, Q[j]);
+        }
+        // horizontal pass: P[k] = (c[k], c[k + NP]) with c[m] = V of pixel m - 2
+        // (pixel m lives in pair m % NP, half m / NP)
+        const float Vm2 = __shfl_up_sync(FULL, hi2(V[NP - 2]), 1), Vm1 = __shfl_up_sync(FULL, hi2(V[NP - 1]), 1);
+        const float Vp0 = __shfl_down_sync(FULL, lo2(V[0]), 1), Vp1 = __shfl_down_sync(FULL, lo2(V[1]), 1);
+        u64 P[NP + 4];
+        P[0] = pk2(Vm2, lo2(V[NP - 2]));   // (V[-2], V[NP-2])
+        P[1] = pk2(Vm1, lo2(V[NP - 1]));   // (V[-1], V[NP-1])
+#pragma unroll
+        for (int j = 0; j < NP; j++) P[j + 2] = V[j];
+        P[NP + 2] = pk2(hi2(V[0]), Vp0);   // (V[NP],   V[NPX])
+        P[NP + 3] = pk2(hi2(V[1]), Vp1);   // (V[NP+1], V[NPX+1])
+        const u64 GH0 = pk2(xp.gh0, xp.gh0), GH1 = pk2(xp.gh1, xp.gh1), GH2 = pk2(xp.gh2, xp.gh2);
+        const u64 BIAS = pk2(kBias, kBias);
+        uint32_t bits[NPX];
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            const u64 e2 = add2(P[j], P[j + 4]), e1 = add2(P[j + 1], P[j + 3]);
+            const u64 u = fma2(GH2, e2, fma2(GH1, e1, mul2(GH0, P[j + 2])));  // S~ of pixels j, j + NP
+            const u64 rr = add2(u, BIAS);
+            bits[j] = lo2u(rr);
+            bits[j + NP] = hi2u(rr);
+        }
+        // guard band: the fraction bits within a ulps of 0 (mod 2^kFracBits)
+        uint32_t z[NPX];
+        uint32_t zmin = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < NPX; j++) z[j] = (bits[j] << (32 - kFracBits)) + xp.zoff;
+#pragma unroll
+        for (int j = 0; j < NPX; j += 2) zmin = __vimin3_u32(zmin, z[j], z[j + 1]);
+#pragma unroll
+        for (int j = 0; j < NPX; j++) bits[j] &= kBiasMask;
+        if (__builtin_expect(__any_sync(FULL, zmin < xp.zthr), 0)) {
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < NPX; j++) mask |= (z[j] < xp.zthr ? 1u : 0u) << j;
+            if (p.slow_counter && mask) atomicAdd(p.slow_counter, (unsigned long long)__popc(mask));
+            const int slot = (int)((geo.ring_cur - geo.ring_warp) / kRowB);
+            __syncwarp();  // the newest ring row was just stored by the other lanes
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const uint32_t v = __float_as_uint(blur_exact_one<NPX>(geo.ring_warp, NPX * lane + j, slot, geo.w25));
+#pragma unroll
+                for (int k = 0; k < NPX; k++)
+                    if (k == j) bits[k] = v;
+            }
+            __syncwarp();  // the ring slot of the oldest row is overwritten by the next step
+        }
+#pragma unroll
+        for (int j = 0; j < NP; j++) F[j] = pk2u(bits[j], bits[j + NP]);
+    } else {
+        const float sc = __uint_as_float(0x7f000000u);  // 2^127: q*2^-149 -> q*2^-22 (a normal float)
+        const u64 SC = pk2(sc, sc);
+#pragma unroll
+        for (int j = 0; j < NP; j++) F[j] = mul2(Q[j], SC);
+    }
+
+    // ---- 3. Sobel, vertical pass first: output row yo = yb-1 reads rows yb-2, yb-1, yb -------------
+    // BORDER_REFLECT_101 in y: row -1 -> row 1 (first output row), row H -> row H-2 (last output row;
+    // this step's input row is a dummy then)
+    if (yb == 1) {
+#pragma unroll
+        for (int j = 0; j < NP; j++) st.F2[j] = F[j];
+    }
+    if (yb == H) {
+#pragma unroll
+        for (int j = 0; j < NP; j++) F[j] = st.F2[j];
+    }
+    const u64 TWO = pk2(2.f, 2.f);
+    u64 Vs[NP], Vd[NP];   // Vs = f(yb-2) + 2 f(yb-1) + f(yb),  Vd = f(yb) - f(yb-2)
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        Vs[j] = fma2(TWO, st.F1[j], add2(st.F2[j], F[j]));
+        Vd[j] = sub2(F[j], st.F2[j]);
+    }
+    // horizontal pass, BORDER_REFLECT_101 in x: gx = Vs[x+1] - Vs[x-1],  gy = Vd[x-1] + 2 Vd[x] + Vd[x+1]
+    float sl = __shfl_up_sync(FULL, hi2(Vs[NP - 1]), 1), sr = __shfl_down_sync(FULL, lo2(Vs[0]), 1);
+    float dl = __shfl_up_sync(FULL, hi2(Vd[NP - 1]), 1), dr = __shfl_down_sync(FULL, lo2(Vd[0]), 1);
+    if (edge) {
+        if (geo.left_edge && lane == 1) { sl = lo2(Vs[1]); dl = lo2(Vd[1]); }                                // x = -1 -> x = 1
+        if (geo.right_edge && lane == geo.lane_last) { sr = hi2(Vs[NP - 2]); dr = hi2(Vd[NP - 2]); }         // x = W  -> x = W-2
+    }
+    // KS[k] = (e[k], e[k + NP]) with e[m] = Vs of pixel m - 1; KD likewise for Vd
+    u64 KS[NP + 2], KD[NP + 2];
+    KS[0] = pk2(sl, lo2(Vs[NP - 1]));
+    KD[0] = pk2(dl, lo2(Vd[NP - 1]));
+#pragma unroll
+    for (int j = 0; j < NP; j++) { KS[j + 1] = Vs[j]; KD[j + 1] = Vd[j]; }
+    KS[NP + 1] = pk2(hi2(Vs[0]), sr);
+    KD[NP + 1] = pk2(hi2(Vd[0]), dr);
+    {
+        // m * OS has the integer round-half-even(m) as its bit pattern (denormal result)
+        const float os = __uint_as_float(BLUR ? 1u /* 2^-149 */ : 0x00400000u /* 2^-127 */);
+        const u64 OS = pk2(os, os);
+        uint32_t q[NPX];
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            const u64 gx = sub2(KS[j + 2], KS[j]);
+            const u64 gy = fma2(TWO, KD[j + 1], add2(KD[j], KD[j + 2]));
+            const u64 m2 = fma2(gx, gx, mul2(gy, gy));
+            const u64 m = mul2(pk2(sqrt_approx(lo2(m2)), sqrt_approx(hi2(m2))), OS);
+            q[j] = lo2u(m);
+            q[j + NP] = hi2u(m);
+        }
+        const uint32_t ok = (r >= geo.r_store && r <= geo.r_last) ? geo.store_lane : 0u;
+        const uint32_t w0 = i2ip(q[1], q[0], i2ip(q[3], q[2], 0u));
+        if constexpr (NPX == 8) {
+            const uint32_t w1 = i2ip(q[5], q[4], i2ip(q[7], q[6], 0u));
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.v2.u32 [%0], {%1, %2};\n\t}"
+                         ::"l"(geo.dst), "r"(w0), "r"(w1), "r"(ok) : "memory");
+        } else {
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}"
+                         ::"l"(geo.dst), "r"(w0), "r"(ok) : "memory");
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        st.F2[j] = st.F1[j];
+        st.F1[j] = F[j];
+    }
+    geo.dst += W;
+}
+
+template <int NPX, int CN, bool BGR, bool BLUR>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, NPX == 8 ? RIP_X2_MINB8 : RIP_X2_MINB4)
+fused_x2_kernel(const __grid_constant__ X2Params xp)
+{
+    constexpr int HALO = BLUR ? 3 : 1;  // input rows above/below an output row
+    constexpr int kRowW = 32 * NPX;     // words per ring row
+    constexpr int kBand = 30 * NPX;
+    const FusedParams &p = xp.f;
+
+    __shared__ __align__(16) uint32_t ring[BLUR ? kWarpsPerBlock * 5 * kRowW : 4];
+    __shared__ float w25s[32];
+    if (threadIdx.x < 25) w25s[threadIdx.x] = p.w[threadIdx.x];
+    __syncthreads();  // the only block-level barrier: the warps are independent from here on
+
+    GeoX geo;
+    geo.lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    geo.ring_warp = (uint32_t)__cvta_generic_to_shared(ring + (BLUR ? warp * 5 * kRowW : 0));
+    geo.ring_cur = geo.ring_warp + NPX * 4 * geo.lane;
+    geo.w25 = (uint32_t)__cvta_generic_to_shared(w25s);
+    int bid = blockIdx.x;
+    const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
+    const int seg = bid % p.n_segs;
+    const int frame = bid / p.n_segs;
+    const int band = bg * kWarpsPerBlock + warp;
+    if (band >= p.n_bands) return;  // warp-uniform
+
+    const int W = p.W;
+    const int xw0 = band * kBand;
+    const int x = xw0 - NPX + NPX * geo.lane;      // first of this lane's pixels
+    const bool in_img = (x >= 0) && (x < W);       // W % NPX == 0: a lane is fully inside or fully outside
+    geo.lane_last = (W - xw0) / NPX;               // lane holding the last NPX pixels of the row (may be > 31)
+    geo.left_edge = (band == 0);
+    geo.right_edge = (geo.lane_last <= 31);
+    const int ys = p.out_row0 + seg * p.seg_rows;
+    const int ye = min(ys + p.seg_rows, p.out_row0 + p.out_rows);
+    geo.r_store = ys + HALO;
+    geo.r_last = ye - 1 + HALO;
+    geo.in_pitch = (uint32_t)W * CN;
+    const uint8_t *in_base = p.in + (size_t)frame * p.in_rows * geo.in_pitch;
+    geo.store_lane = ((geo.lane >= 1) && (geo.lane <= 30) && in_img) ? 1u : 0u;
+
+    WarpX<NPX, CN> st;
+#pragma unroll
+    for (int j = 0; j < NPX / 2; j++) st.a0[j] = st.a1[j] = st.a2[j] = st.a3[j] = st.F1[j] = st.F2[j] = 0ull;
+
+    // Rows are clamped to the rows the input band holds.  The host guarantees the band covers every
+    // row an output needs, and that it starts at row 0 / ends at row H-1 wherever the clamp-to-edge rule
+    // (GaussianBlur.cpp:241) is actually exercised; other clamped rows are read-ahead only.
+    int r = ys - HALO;
+    const uint32_t xoff = in_img ? (uint32_t)x * CN : 0u;
+    RawX<NPX, CN> b0, b1, b2;   // rows r, r+1, r+2
+    {
+        const int i0 = min(max(r - p.in_row0, 0), p.in_rows - 1), i1 = min(max(r + 1 - p.in_row0, 0), p.in_rows - 1),
+                  i2 = min(max(r + 2 - p.in_row0, 0), p.in_rows - 1);
+        load_row_x2<NPX, CN>(b0, in_base + (size_t)i0 * geo.in_pitch + xoff);
+        load_row_x2<NPX, CN>(b1, in_base + (size_t)i1 * geo.in_pitch + xoff);
+        geo.src = in_base + (size_t)i2 * geo.in_pitch + xoff;
+        load_row_x2<NPX, CN>(b2, geo.src);
+    }
+    // step r loads row r + 3 = one past the row src points at: advance iff in_row0 <= r + 2 < in_row0 + in_rows - 1
+    geo.adv_lo = p.in_row0 - 2;
+    geo.adv_n = p.in_rows - 1;
+    // output row produced by the step of input row r is r - HALO
+    geo.dst = p.out + (size_t)frame * p.out_rows * W + (ptrdiff_t)(r - HALO - p.out_row0) * W + x;
+
+    // three rows per trip; up to two trailing steps past r_last compute nothing that is stored
+#pragma unroll 1
+    for (; r <= geo.r_last; r += 3) {
+        step_x2<NPX, CN, BGR, BLUR>(st, b0, xp, geo, r);
+        step_x2<NPX, CN, BGR, BLUR>(st, b1, xp, geo, r + 1);
+        step_x2<NPX, CN, BGR, BLUR>(st, b2, xp, geo, r + 2);
+    }
+}
