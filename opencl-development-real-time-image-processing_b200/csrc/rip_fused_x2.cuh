@@ -102,14 +102,36 @@ __device__ __forceinline__ uint32_t gray_x2(const uint32_t *w, u64 *Q, u64 *E)
     return any;
 }
 
-// Cold, out of line: for the pixels flagged in `m` (t is a multiple of 1000) look up the (r,g)-indexed bit
-// that says whether the reference's double evaluation lands one below t/1000.  Scalar arguments only
-// (they travel in registers); returns the mask of pixels whose gray must be decremented.
-template <int CN, bool BGR>
-__device__ __noinline__ uint32_t gray_down_mask(uint32_t m, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
-                                                uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_b64(uint32_t addr, u64 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+
+// The cold paths below never write a register the hot path reads: they patch a copy of the lane's pairs
+// in shared memory (pair layout: word 2j = pixel j, word 2j+1 = pixel j + NPX/2) and the hot path
+// reloads the pairs with loads predicated on "this lane was flagged".  A cold block that modified the
+// hot registers in place would make every one of them a phi and cost ~30 register moves per row.
+template <int NP>
+__device__ __forceinline__ void reload_pairs_if(u64 *v, uint32_t addr, uint32_t flag)
 {
-    uint32_t out = 0;
+    if constexpr (NP == 4) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.shared.b64 %0, [%4];\n\t@p ld.shared.b64 %1, [%4+8];\n\t"
+                     "@p ld.shared.b64 %2, [%4+16];\n\t@p ld.shared.b64 %3, [%4+24];\n\t}"
+                     : "+l"(v[0]), "+l"(v[1]), "+l"(v[2]), "+l"(v[3]) : "r"(addr), "r"(flag) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.b64 %0, [%2];\n\t@p ld.shared.b64 %1, [%2+8];\n\t}"
+                     : "+l"(v[0]), "+l"(v[1]) : "r"(addr), "r"(flag) : "memory");
+    }
+}
+
+// Cold, out of line: for the pixels flagged in `m` (t is a multiple of 1000) look up the (r,g)-indexed bit
+// that says whether the reference's double evaluation lands one below t/1000, and decrement the copy of
+// that pixel's gray at `pairs` (shared memory).  Scalar arguments only (they travel in registers).
+template <int NPX, int CN, bool BGR>
+__device__ __noinline__ void gray_patch(uint32_t m, uint32_t pairs, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+                                        uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7)
+{
+    constexpr int NP = NPX / 2;
     while (m) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
@@ -119,22 +141,42 @@ __device__ __noinline__ uint32_t gray_down_mask(uint32_t m, uint32_t w0, uint32_
         const uint32_t px = __byte_perm(lo, hi, 0x3210u + 0x1111u * (uint32_t)(off & 3));  // channel bytes in bits 0..23
         const uint32_t r = BGR ? (px >> 16) & 0xffu : px & 0xffu, g = (px >> 8) & 0xffu;
         const uint32_t idx = (r << 8) | g;
-        out |= ((__ldg(&d_gray_down[idx >> 5]) >> (idx & 31u)) & 1u) << j;
+        const uint32_t down = (__ldg(&d_gray_down[idx >> 5]) >> (idx & 31u)) & 1u;
+        const uint32_t a = pairs + 4u * (uint32_t)(2 * (j % NP) + j / NP);
+        sts_u32(a, lds_u32(a) - down);
     }
-    return out;
 }
 
-template <int NPX, int CN, bool BGR>
-__device__ __forceinline__ void gray_fix_x2(const uint32_t *w, u64 *Q, const u64 *E)
+// flagged-pixel mask of a lane from the E pairs of gray_x2 (bit j = pixel j)
+template <int NPX>
+__device__ __forceinline__ uint32_t gray_flag_mask(const u64 *E)
 {
-    constexpr int NP = NPX / 2, NW = NPX * CN / 4;
+    constexpr int NP = NPX / 2;
     uint32_t m = 0;
 #pragma unroll
     for (int j = 0; j < NP; j++) m |= ((lo2u(E[j]) & 1u) << j) | ((hi2u(E[j]) & 1u) << (j + NP));
-    const uint32_t d = gray_down_mask<CN, BGR>(m, w[0], w[1], w[2], NW > 3 ? w[NW > 3 ? 3 : 0] : 0u, NW > 4 ? w[NW > 4 ? 4 : 0] : 0u,
-                                               NW > 5 ? w[NW > 5 ? 5 : 0] : 0u, NW > 6 ? w[NW > 6 ? 6 : 0] : 0u, NW > 7 ? w[NW > 7 ? 7 : 0] : 0u);
+    return m;
+}
+
+template <int NPX, int CN, bool BGR>
+__device__ __forceinline__ void gray_patch_call(uint32_t m, uint32_t pairs, const uint32_t *w)
+{
+    constexpr int NW = NPX * CN / 4;
+    gray_patch<NPX, CN, BGR>(m, pairs, w[0], w[1], w[2], NW > 3 ? w[NW > 3 ? 3 : 0] : 0u, NW > 4 ? w[NW > 4 ? 4 : 0] : 0u,
+                             NW > 5 ? w[NW > 5 ? 5 : 0] : 0u, NW > 6 ? w[NW > 6 ? 6 : 0] : 0u, NW > 7 ? w[NW > 7 ? 7 : 0] : 0u);
+}
+
+// register-only variant for the self-test (not used by the kernel)
+template <int NPX, int CN, bool BGR>
+__device__ __forceinline__ void gray_fix_x2(const uint32_t *w, u64 *Q, const u64 *E)
+{
+    constexpr int NP = NPX / 2;
+    __shared__ uint32_t scratch[256 * NPX];
+    const uint32_t pairs = (uint32_t)__cvta_generic_to_shared(scratch + threadIdx.x * NPX);
 #pragma unroll
-    for (int j = 0; j < NP; j++) Q[j] = pk2u(lo2u(Q[j]) - ((d >> j) & 1u), hi2u(Q[j]) - ((d >> (j + NP)) & 1u));
+    for (int j = 0; j < NP; j++) sts_b64(pairs + 8 * j, Q[j]);
+    gray_patch_call<NPX, CN, BGR>(gray_flag_mask<NPX>(E), pairs, w);
+    reload_pairs_if<NP>(Q, pairs, 1u);
 }
 
 template <int NPX, int CN>
@@ -176,32 +218,30 @@ struct GeoX {
     const uint8_t *src;      // this lane's pixels in the input row that was loaded last
     uint8_t *dst;            // this lane's pixels in the output row produced next
     uint32_t ring_warp;      // shared-memory byte address of this warp's gray ring [5][32*NPX] (integer gray;
-                             // within a lane's NPX words the pixels sit in register order: pairs (j, j+NPX/2))
+                             // within a lane's NPX words the pixels sit in pair order, see reload_pairs_if)
     uint32_t ring_cur;       // byte address of this lane's words in the ring row holding the newest gray row
+    uint32_t patch;          // byte address of this lane's NPX words of scratch for the cold paths
     uint32_t w25;            // shared-memory byte address of the exact 2-D weights (for the replay)
     uint32_t in_pitch;
     int adv_lo, adv_n;       // the source pointer advances before the load of step r iff 0 <= r - adv_lo < adv_n
-    int lane, lane_last;
-    bool left_edge, right_edge;
+    int lane;
+    int cmin, cmax;          // first / last column of the band (0 = pixel 0 of lane 0) that lies inside the image
+    bool e_left, e_right;    // this lane holds image column 0 / W-1 (border rules in x apply to it)
     uint32_t store_lane;
     int r_store, r_last;     // first / last step that produces an output row
 };
 
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
-
 // Cold, out of line: the reference's 25-tap sum (GaussianBlur.cpp:236-258) for ONE pixel, column `c`
-// of the warp's band (0 = pixel 0 of lane 0): ky-major / kx-minor from 0.0f, unfused multiply and
-// add, clamp, truncate.  Returns the biased value kBias + b.  Columns outside the band are clamped:
-// they only feed blurred values of the halo lanes that no stored output consumes.
+// of the warp's band: ky-major / kx-minor from 0.0f, unfused multiply and add, clamp, truncate.
+// Columns are clamped to [cmin, cmax] (clamp-to-edge, GaussianBlur.cpp:240).  Returns kBias + b.
 template <int NPX>
-__device__ __noinline__ float blur_exact_one(uint32_t ring_warp, int c, int slot_new, uint32_t w25)
+__device__ __noinline__ float blur_exact_one(uint32_t ring_warp, int c, int cmin, int cmax, int slot_new, uint32_t w25)
 {
     constexpr int NP = NPX / 2;
     uint32_t col[5];
 #pragma unroll
     for (int kx = 0; kx < 5; kx++) {
-        const int cc = min(max(c + kx - 2, 0), 32 * NPX - 1);
+        const int cc = min(max(c + kx - 2, cmin), cmax);
         const int k = cc % NPX;
         col[kx] = ring_warp + 4u * (uint32_t)((cc - k) + 2 * (k % NP) + k / NP);
     }
@@ -218,25 +258,40 @@ __device__ __noinline__ float blur_exact_one(uint32_t ring_warp, int c, int slot
 }
 
 // One image row of the sliding window: consumes the input row held in `buf` (row r, clamped to the
-// rows of the band), refills `buf` with row r + 3, and -- for kRstore <= r <= r_last -- stores output
-// row r - HALO.  The border rules are applied at run time (a few uniform branches per row), so this is
-// the only copy of the row body; the caller unrolls it by three with three row buffers, which makes
-// the buffer rotation and the two-row Sobel delay line pure register renames.
+// rows of the band), refills `buf` with row r + 3, and -- for r_store <= r <= r_last -- stores output
+// row r - HALO.  The border rules are applied at run time (per-lane selects in x, two rare uniform
+// branches in y), so this is the only copy of the row body; the caller unrolls it by three with three
+// row buffers, which makes the buffer rotation and the two-row Sobel delay line register renames.
 template <int NPX, int CN, bool BGR, bool BLUR>
 __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, const X2Params &xp, GeoX &geo, int r)
 {
     constexpr int NP = NPX / 2;
     constexpr int kRowB = 32 * NPX * 4;  // bytes per ring row
     const FusedParams &p = xp.f;
-    const int W = p.W, H = p.H, lane = geo.lane;
-    const bool edge = geo.left_edge || geo.right_edge;
+    const int W = p.W, H = p.H;
 
     // ---- 1. gray of row r; refill the buffer with row r + 3 ---------------------------------------
     u64 Q[NP];
     {
         u64 E[NP];
-        const uint32_t any = gray_x2<NPX, CN, BGR>(buf.w, Q, E);
-        if (__builtin_expect(__any_sync(FULL, any & 1u), 0)) gray_fix_x2<NPX, CN, BGR>(buf.w, Q, E);
+        const uint32_t flagged = gray_x2<NPX, CN, BGR>(buf.w, Q, E) & 1u;
+        uint32_t pairs = geo.patch;
+        if constexpr (BLUR) {
+            // park the integer gray row in the shared ring (the exact replay reads it back)
+            geo.ring_cur += kRowB;
+            if (geo.ring_cur >= geo.ring_warp + 5 * kRowB) geo.ring_cur -= 5 * kRowB;
+            pairs = geo.ring_cur;
+#pragma unroll
+            for (int j = 0; j < NP; j++) sts_b64(pairs + 8 * j, Q[j]);
+        }
+        if (__builtin_expect(__any_sync(FULL, flagged), 0)) {
+            if constexpr (!BLUR) {
+#pragma unroll
+                for (int j = 0; j < NP; j++) sts_b64(pairs + 8 * j, Q[j]);
+            }
+            gray_patch_call<NPX, CN, BGR>(gray_flag_mask<NPX>(E), pairs, buf.w);
+        }
+        reload_pairs_if<NP>(Q, pairs, flagged);
         if ((unsigned)(r - geo.adv_lo) < (unsigned)geo.adv_n) geo.src += geo.in_pitch;
         load_row_x2<NPX, CN>(buf, geo.src);
     }
@@ -246,24 +301,6 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
     u64 F[NP];
     const int yb = BLUR ? r - 2 : r;
     if constexpr (BLUR) {
-        if (edge) {  // clamp-to-edge columns (GaussianBlur.cpp:240)
-            const uint32_t first = __shfl_sync(FULL, lo2u(Q[0]), 1);
-            const uint32_t last = __shfl_sync(FULL, hi2u(Q[NP - 1]), min(geo.lane_last, 31));
-            if (geo.left_edge && lane == 0) {
-#pragma unroll
-                for (int j = 0; j < NP; j++) Q[j] = pk2u(first, first);
-            }
-            if (geo.right_edge && lane > geo.lane_last) {
-#pragma unroll
-                for (int j = 0; j < NP; j++) Q[j] = pk2u(last, last);
-            }
-        }
-        // park the integer gray row in the shared ring (only the cold exact replay reads it back)
-        geo.ring_cur += kRowB;
-        if (geo.ring_cur >= geo.ring_warp + 5 * kRowB) geo.ring_cur -= 5 * kRowB;
-#pragma unroll
-        for (int j = 0; j < NP; j += 2)
-            asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(geo.ring_cur + 8 * j), "l"(Q[j]), "l"(Q[j + 1]) : "memory");
         // vertical pass, accumulate form: row r completes blurred row r-2
         const u64 GV0 = pk2(xp.gv0, xp.gv0), GV1 = pk2(xp.gv1, xp.gv1), GV2 = pk2(xp.gv2, xp.gv2);
         u64 V[NP];
@@ -275,10 +312,15 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
             st.a2[j] = fma2(GV1, Q[j], st.a3[j]);
             st.a3[j] = mul2(GV2, Q[j]);
         }
-        // horizontal pass: P[k] = (c[k], c[k + NP]) with c[m] = V of pixel m - 2
-        // (pixel m lives in pair m % NP, half m / NP)
-        const float Vm2 = __shfl_up_sync(FULL, hi2(V[NP - 2]), 1), Vm1 = __shfl_up_sync(FULL, hi2(V[NP - 1]), 1);
-        const float Vp0 = __shfl_down_sync(FULL, lo2(V[0]), 1), Vp1 = __shfl_down_sync(FULL, lo2(V[1]), 1);
+        // horizontal pass: P[k] = (c[k], c[k + NP]) with c[m] = V of pixel m - 2 (pixel m lives in
+        // pair m % NP, half m / NP).  Clamp-to-edge columns (GaussianBlur.cpp:240): V is linear in the
+        // gray column, so the clamp applies to V: left of column 0 / right of column W-1 repeat it.
+        float Vm2 = __shfl_up_sync(FULL, hi2(V[NP - 2]), 1), Vm1 = __shfl_up_sync(FULL, hi2(V[NP - 1]), 1);
+        float Vp0 = __shfl_down_sync(FULL, lo2(V[0]), 1), Vp1 = __shfl_down_sync(FULL, lo2(V[1]), 1);
+        Vm2 = geo.e_left ? lo2(V[0]) : Vm2;
+        Vm1 = geo.e_left ? lo2(V[0]) : Vm1;
+        Vp0 = geo.e_right ? hi2(V[NP - 1]) : Vp0;
+        Vp1 = geo.e_right ? hi2(V[NP - 1]) : Vp1;
         u64 P[NP + 4];
         P[0] = pk2(Vm2, lo2(V[NP - 2]));   // (V[-2], V[NP-2])
         P[1] = pk2(Vm1, lo2(V[NP - 1]));   // (V[-1], V[NP-1])
@@ -288,43 +330,41 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
         P[NP + 3] = pk2(hi2(V[1]), Vp1);   // (V[NP+1], V[NPX+1])
         const u64 GH0 = pk2(xp.gh0, xp.gh0), GH1 = pk2(xp.gh1, xp.gh1), GH2 = pk2(xp.gh2, xp.gh2);
         const u64 BIAS = pk2(kBias, kBias);
-        uint32_t bits[NPX];
 #pragma unroll
         for (int j = 0; j < NP; j++) {
             const u64 e2 = add2(P[j], P[j + 4]), e1 = add2(P[j + 1], P[j + 3]);
             const u64 u = fma2(GH2, e2, fma2(GH1, e1, mul2(GH0, P[j + 2])));  // S~ of pixels j, j + NP
-            const u64 rr = add2(u, BIAS);
-            bits[j] = lo2u(rr);
-            bits[j + NP] = hi2u(rr);
+            F[j] = add2(u, BIAS);                                            // floor(S~) in bits 15..22, fraction below
         }
         // guard band: the fraction bits within a ulps of 0 (mod 2^kFracBits)
-        uint32_t z[NPX];
         uint32_t zmin = 0xffffffffu;
 #pragma unroll
-        for (int j = 0; j < NPX; j++) z[j] = (bits[j] << (32 - kFracBits)) + xp.zoff;
-#pragma unroll
-        for (int j = 0; j < NPX; j += 2) zmin = __vimin3_u32(zmin, z[j], z[j + 1]);
-#pragma unroll
-        for (int j = 0; j < NPX; j++) bits[j] &= kBiasMask;
-        if (__builtin_expect(__any_sync(FULL, zmin < xp.zthr), 0)) {
+        for (int j = 0; j < NP; j++)
+            zmin = __vimin3_u32(zmin, (lo2u(F[j]) << (32 - kFracBits)) + xp.zoff, (hi2u(F[j]) << (32 - kFracBits)) + xp.zoff);
+        const uint32_t flagged = zmin < xp.zthr ? 1u : 0u;
+        if (__builtin_expect(__any_sync(FULL, flagged), 0)) {
             uint32_t mask = 0;
 #pragma unroll
-            for (int j = 0; j < NPX; j++) mask |= (z[j] < xp.zthr ? 1u : 0u) << j;
+            for (int j = 0; j < NP; j++) {
+                mask |= (((lo2u(F[j]) << (32 - kFracBits)) + xp.zoff) < xp.zthr ? 1u : 0u) << j;
+                mask |= (((hi2u(F[j]) << (32 - kFracBits)) + xp.zoff) < xp.zthr ? 1u : 0u) << (j + NP);
+            }
             if (p.slow_counter && mask) atomicAdd(p.slow_counter, (unsigned long long)__popc(mask));
             const int slot = (int)((geo.ring_cur - geo.ring_warp) / kRowB);
+#pragma unroll
+            for (int j = 0; j < NP; j++) sts_b64(geo.patch + 8 * j, F[j]);
             __syncwarp();  // the newest ring row was just stored by the other lanes
             while (mask) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
-                const uint32_t v = __float_as_uint(blur_exact_one<NPX>(geo.ring_warp, NPX * lane + j, slot, geo.w25));
-#pragma unroll
-                for (int k = 0; k < NPX; k++)
-                    if (k == j) bits[k] = v;
+                const float v = blur_exact_one<NPX>(geo.ring_warp, NPX * geo.lane + j, geo.cmin, geo.cmax, slot, geo.w25);
+                sts_u32(geo.patch + 4u * (uint32_t)(2 * (j % NP) + j / NP), __float_as_uint(v));
             }
             __syncwarp();  // the ring slot of the oldest row is overwritten by the next step
         }
+        reload_pairs_if<NP>(F, geo.patch, flagged);
 #pragma unroll
-        for (int j = 0; j < NP; j++) F[j] = pk2u(bits[j], bits[j + NP]);
+        for (int j = 0; j < NP; j++) F[j] = pk2u(lo2u(F[j]) & kBiasMask, hi2u(F[j]) & kBiasMask);   // kBias + floor(S)
     } else {
         const float sc = __uint_as_float(0x7f000000u);  // 2^127: q*2^-149 -> q*2^-22 (a normal float)
         const u64 SC = pk2(sc, sc);
@@ -334,12 +374,15 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
 
     // ---- 3. Sobel, vertical pass first: output row yo = yb-1 reads rows yb-2, yb-1, yb -------------
     // BORDER_REFLECT_101 in y: row -1 -> row 1 (first output row), row H -> row H-2 (last output row;
-    // this step's input row is a dummy then)
-    if (yb == 1) {
+    // this step's input row is a dummy then).  The empty volatile asm keeps these two rare, warp-uniform
+    // cases real branches instead of 2*NPX selects per row.
+    if (__builtin_expect(yb == 1, 0)) {
+        asm volatile("" ::: "memory");
 #pragma unroll
         for (int j = 0; j < NP; j++) st.F2[j] = F[j];
     }
-    if (yb == H) {
+    if (__builtin_expect(yb == H, 0)) {
+        asm volatile("" ::: "memory");
 #pragma unroll
         for (int j = 0; j < NP; j++) F[j] = st.F2[j];
     }
@@ -353,10 +396,10 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
     // horizontal pass, BORDER_REFLECT_101 in x: gx = Vs[x+1] - Vs[x-1],  gy = Vd[x-1] + 2 Vd[x] + Vd[x+1]
     float sl = __shfl_up_sync(FULL, hi2(Vs[NP - 1]), 1), sr = __shfl_down_sync(FULL, lo2(Vs[0]), 1);
     float dl = __shfl_up_sync(FULL, hi2(Vd[NP - 1]), 1), dr = __shfl_down_sync(FULL, lo2(Vd[0]), 1);
-    if (edge) {
-        if (geo.left_edge && lane == 1) { sl = lo2(Vs[1]); dl = lo2(Vd[1]); }                                // x = -1 -> x = 1
-        if (geo.right_edge && lane == geo.lane_last) { sr = hi2(Vs[NP - 2]); dr = hi2(Vd[NP - 2]); }         // x = W  -> x = W-2
-    }
+    sl = geo.e_left ? lo2(Vs[1]) : sl;             // x = -1 -> x = 1
+    dl = geo.e_left ? lo2(Vd[1]) : dl;
+    sr = geo.e_right ? hi2(Vs[NP - 2]) : sr;       // x = W  -> x = W-2
+    dr = geo.e_right ? hi2(Vd[NP - 2]) : dr;
     // KS[k] = (e[k], e[k + NP]) with e[m] = Vs of pixel m - 1; KD likewise for Vd
     u64 KS[NP + 2], KD[NP + 2];
     KS[0] = pk2(sl, lo2(Vs[NP - 1]));
@@ -408,6 +451,7 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     const FusedParams &p = xp.f;
 
     __shared__ __align__(16) uint32_t ring[BLUR ? kWarpsPerBlock * 5 * kRowW : 4];
+    __shared__ __align__(16) uint32_t patch[kWarpsPerBlock * kRowW];
     __shared__ float w25s[32];
     if (threadIdx.x < 25) w25s[threadIdx.x] = p.w[threadIdx.x];
     __syncthreads();  // the only block-level barrier: the warps are independent from here on
@@ -417,6 +461,7 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     const int warp = threadIdx.x >> 5;
     geo.ring_warp = (uint32_t)__cvta_generic_to_shared(ring + (BLUR ? warp * 5 * kRowW : 0));
     geo.ring_cur = geo.ring_warp + NPX * 4 * geo.lane;
+    geo.patch = (uint32_t)__cvta_generic_to_shared(patch + threadIdx.x * NPX);
     geo.w25 = (uint32_t)__cvta_generic_to_shared(w25s);
     int bid = blockIdx.x;
     const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
@@ -429,9 +474,11 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     const int xw0 = band * kBand;
     const int x = xw0 - NPX + NPX * geo.lane;      // first of this lane's pixels
     const bool in_img = (x >= 0) && (x < W);       // W % NPX == 0: a lane is fully inside or fully outside
-    geo.lane_last = (W - xw0) / NPX;               // lane holding the last NPX pixels of the row (may be > 31)
-    geo.left_edge = (band == 0);
-    geo.right_edge = (geo.lane_last <= 31);
+    const int lane_last = (W - xw0) / NPX;         // lane holding the last NPX pixels of the row (may be > 31)
+    geo.e_left = (band == 0) && geo.lane == 1;
+    geo.e_right = geo.lane == lane_last;
+    geo.cmin = band == 0 ? NPX : 0;
+    geo.cmax = min(lane_last, 31) * NPX + NPX - 1;
     const int ys = p.out_row0 + seg * p.seg_rows;
     const int ye = min(ys + p.seg_rows, p.out_row0 + p.out_rows);
     geo.r_store = ys + HALO;
