@@ -38,8 +38,8 @@ __device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0,
 __device__ __forceinline__ u64 pk2u(uint32_t lo, uint32_t hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
 __device__ __forceinline__ float lo2(u64 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
 __device__ __forceinline__ float hi2(u64 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
-__device__ __forceinline__ uint32_t lo2u(u64 v) { return (uint32_t)v; }
-__device__ __forceinline__ uint32_t hi2u(u64 v) { return (uint32_t)(v >> 32); }
+__device__ __forceinline__ uint32_t lo2u(u64 v) { uint32_t lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ uint32_t hi2u(u64 v) { uint32_t lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); return hi; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
@@ -111,72 +111,74 @@ __device__ __forceinline__ void sts_b64(uint32_t addr, u64 v) { asm volatile("st
 // in shared memory (pair layout: word 2j = pixel j, word 2j+1 = pixel j + NPX/2) and the hot path
 // reloads the pairs with loads predicated on "this lane was flagged".  A cold block that modified the
 // hot registers in place would make every one of them a phi and cost ~30 register moves per row.
-template <int NP>
+// STRIDE = bytes between consecutive pairs: 8 in the gray ring (dense), 16 in the scratch copies (so that
+// ptxas cannot merge their 64-bit stores into 128-bit ones, which need consecutive registers and cost moves
+// that it hoists onto the hot path)
+template <int NP, int STRIDE>
 __device__ __forceinline__ void reload_pairs_if(u64 *v, uint32_t addr, uint32_t flag)
 {
     if constexpr (NP == 4) {
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.shared.b64 %0, [%4];\n\t@p ld.shared.b64 %1, [%4+8];\n\t"
-                     "@p ld.shared.b64 %2, [%4+16];\n\t@p ld.shared.b64 %3, [%4+24];\n\t}"
-                     : "+l"(v[0]), "+l"(v[1]), "+l"(v[2]), "+l"(v[3]) : "r"(addr), "r"(flag) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.shared.b64 %0, [%4];\n\t@p ld.shared.b64 %1, [%4+%6];\n\t"
+                     "@p ld.shared.b64 %2, [%4+%7];\n\t@p ld.shared.b64 %3, [%4+%8];\n\t}"
+                     : "+l"(v[0]), "+l"(v[1]), "+l"(v[2]), "+l"(v[3]) : "r"(addr), "r"(flag), "n"(STRIDE), "n"(2 * STRIDE), "n"(3 * STRIDE) : "memory");
     } else {
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.b64 %0, [%2];\n\t@p ld.shared.b64 %1, [%2+8];\n\t}"
-                     : "+l"(v[0]), "+l"(v[1]) : "r"(addr), "r"(flag) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.b64 %0, [%2];\n\t@p ld.shared.b64 %1, [%2+%4];\n\t}"
+                     : "+l"(v[0]), "+l"(v[1]) : "r"(addr), "r"(flag), "n"(STRIDE) : "memory");
     }
 }
 
-// Cold, out of line: for the pixels flagged in `m` (t is a multiple of 1000) look up the (r,g)-indexed bit
-// that says whether the reference's double evaluation lands one below t/1000, and decrement the copy of
-// that pixel's gray at `pairs` (shared memory).  Scalar arguments only (they travel in registers).
-template <int NPX, int CN, bool BGR>
-__device__ __noinline__ void gray_patch(uint32_t m, uint32_t pairs, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
-                                        uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7)
+// byte offset of pixel j's word inside a lane's copy of NPX/2 pairs
+template <int NPX, int STRIDE>
+__device__ __forceinline__ uint32_t pair_off(uint32_t j) { return (j & (NPX / 2 - 1)) * STRIDE + (j / (NPX / 2)) * 4u; }
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+
+// Cold (inline on purpose: a call would make ptxas shuffle the hot registers that sit in the callee's
+// argument registers, on the hot path): for the pixels flagged in `m` (t is a multiple of 1000) look up
+// the (r,g)-indexed bit that says whether the reference's double evaluation lands one below t/1000, and
+// decrement the copy of that pixel's gray at `pairs`.  `raw` is a shared-memory copy of the lane's
+// input bytes, so a run-time pixel index needs no select chains.
+template <int NPX, int CN, bool BGR, int STRIDE>
+__device__ __forceinline__ void gray_patch(uint32_t m, uint32_t pairs, uint32_t raw)
 {
-    constexpr int NP = NPX / 2;
+#pragma unroll 1
     while (m) {
-        const int j = __ffs(m) - 1;
+        const uint32_t j = (uint32_t)__ffs(m) - 1u;
         m &= m - 1;
-        const int off = CN * j, wi = off >> 2;
-        const uint32_t lo = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : wi == 3 ? w3 : wi == 4 ? w4 : wi == 5 ? w5 : wi == 6 ? w6 : w7;
-        const uint32_t hi = wi == 0 ? w1 : wi == 1 ? w2 : wi == 2 ? w3 : wi == 3 ? w4 : wi == 4 ? w5 : wi == 5 ? w6 : w7;
-        const uint32_t px = __byte_perm(lo, hi, 0x3210u + 0x1111u * (uint32_t)(off & 3));  // channel bytes in bits 0..23
-        const uint32_t r = BGR ? (px >> 16) & 0xffu : px & 0xffu, g = (px >> 8) & 0xffu;
+        const uint32_t r = lds_u8(raw + CN * j + (BGR ? 2 : 0)), g = lds_u8(raw + CN * j + 1);
         const uint32_t idx = (r << 8) | g;
         const uint32_t down = (__ldg(&d_gray_down[idx >> 5]) >> (idx & 31u)) & 1u;
-        const uint32_t a = pairs + 4u * (uint32_t)(2 * (j % NP) + j / NP);
+        const uint32_t a = pairs + pair_off<NPX, STRIDE>(j);
         sts_u32(a, lds_u32(a) - down);
     }
 }
 
-// flagged-pixel mask of a lane from the E pairs of gray_x2 (bit j = pixel j)
+// flagged-pixel mask of a lane from the E pairs of gray_x2 (bit j = pixel j).  Every half of E is 1
+// (flagged), +0 or -0, so a shift-add chain collects the bits (the sign bit of a -0 either leaves the
+// word or lands in bit 31, which the final mask drops).
 template <int NPX>
 __device__ __forceinline__ uint32_t gray_flag_mask(const u64 *E)
 {
     constexpr int NP = NPX / 2;
     uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < NP; j++) m |= ((lo2u(E[j]) & 1u) << j) | ((hi2u(E[j]) & 1u) << (j + NP));
-    return m;
+    for (int j = 0; j < NP; j++) m += (lo2u(E[j]) << j) + (hi2u(E[j]) << (j + NP));
+    return m & ((1u << NPX) - 1u);
 }
 
-template <int NPX, int CN, bool BGR>
-__device__ __forceinline__ void gray_patch_call(uint32_t m, uint32_t pairs, const uint32_t *w)
-{
-    constexpr int NW = NPX * CN / 4;
-    gray_patch<NPX, CN, BGR>(m, pairs, w[0], w[1], w[2], NW > 3 ? w[NW > 3 ? 3 : 0] : 0u, NW > 4 ? w[NW > 4 ? 4 : 0] : 0u,
-                             NW > 5 ? w[NW > 5 ? 5 : 0] : 0u, NW > 6 ? w[NW > 6 ? 6 : 0] : 0u, NW > 7 ? w[NW > 7 ? 7 : 0] : 0u);
-}
-
-// register-only variant for the self-test (not used by the kernel)
+// register-in / register-out variant for the self-test (not used by the kernel)
 template <int NPX, int CN, bool BGR>
 __device__ __forceinline__ void gray_fix_x2(const uint32_t *w, u64 *Q, const u64 *E)
 {
-    constexpr int NP = NPX / 2;
-    __shared__ uint32_t scratch[256 * NPX];
-    const uint32_t pairs = (uint32_t)__cvta_generic_to_shared(scratch + threadIdx.x * NPX);
+    constexpr int NP = NPX / 2, NW = NPX * CN / 4;
+    __shared__ __align__(16) uint32_t scratch[256 * 3 * NPX];
+    const uint32_t pairs = (uint32_t)__cvta_generic_to_shared(scratch + threadIdx.x * 3 * NPX), raw = pairs + 8 * NPX;
 #pragma unroll
-    for (int j = 0; j < NP; j++) sts_b64(pairs + 8 * j, Q[j]);
-    gray_patch_call<NPX, CN, BGR>(gray_flag_mask<NPX>(E), pairs, w);
-    reload_pairs_if<NP>(Q, pairs, 1u);
+    for (int j = 0; j < NP; j++) sts_b64(pairs + 16 * j, Q[j]);
+#pragma unroll
+    for (int k = 0; k < NW; k++) sts_u32(raw + 4 * k, w[k]);
+    gray_patch<NPX, CN, BGR, 16>(gray_flag_mask<NPX>(E), pairs, raw);
+    reload_pairs_if<NP, 16>(Q, pairs, 1u);
 }
 
 template <int NPX, int CN>
@@ -231,30 +233,46 @@ struct GeoX {
     int r_store, r_last;     // first / last step that produces an output row
 };
 
-// Cold, out of line: the reference's 25-tap sum (GaussianBlur.cpp:236-258) for ONE pixel, column `c`
-// of the warp's band: ky-major / kx-minor from 0.0f, unfused multiply and add, clamp, truncate.
-// Columns are clamped to [cmin, cmax] (clamp-to-edge, GaussianBlur.cpp:240).  Returns kBias + b.
+// Cold (inline, see gray_patch): exact replay for the pixels of one lane that sit inside the guard band.
+// `patch` holds a copy of the lane's NPX biased sums S~ + kBias (pair order); every pixel whose fraction
+// bits are within the band is replaced there by kBias + floor(reference sum): the reference's 25-tap sum
+// (GaussianBlur.cpp:236-258), ky-major / kx-minor from 0.0f, unfused multiply and add, clamp, truncate,
+// read from the warp's gray ring.  Columns are clamped to [cmin, cmax] (clamp-to-edge, GaussianBlur.cpp:240).
+// Kept small (row loop rolled) because three copies of it sit inside the hot loop's address range.
 template <int NPX>
-__device__ __noinline__ float blur_exact_one(uint32_t ring_warp, int c, int cmin, int cmax, int slot_new, uint32_t w25)
+__device__ __forceinline__ void blur_replay_lane(uint32_t patch, uint32_t ring_warp, uint32_t ring_cur, uint32_t w25, int cmin, int cmax,
+                                                 uint32_t zoff, uint32_t zthr, unsigned long long *slow_counter)
 {
-    constexpr int NP = NPX / 2;
-    uint32_t col[5];
+    constexpr uint32_t kRowB = 32 * NPX * 4;
+    const int lane = threadIdx.x & 31;
+    const uint32_t ring_end = ring_warp + 5 * kRowB;
+    const uint32_t row_new = ring_warp + ((ring_cur - ring_warp) / kRowB) * kRowB;   // start of the newest ring row
+    int n = 0;
+#pragma unroll 1
+    for (uint32_t j = 0; j < NPX; j++) {
+        const uint32_t a = patch + pair_off<NPX, 16>(j);
+        if (((lds_u32(a) << (32 - kFracBits)) + zoff) >= zthr) continue;
+        n++;
+        const int c = NPX * lane + (int)j;
+        uint32_t col[5];   // byte offset of columns x-2 .. x+2 inside a ring row
 #pragma unroll
-    for (int kx = 0; kx < 5; kx++) {
-        const int cc = min(max(c + kx - 2, cmin), cmax);
-        const int k = cc % NPX;
-        col[kx] = ring_warp + 4u * (uint32_t)((cc - k) + 2 * (k % NP) + k / NP);
+        for (int kx = 0; kx < 5; kx++) {
+            const uint32_t cc = (uint32_t)min(max(c + kx - 2, cmin), cmax);
+            col[kx] = 4u * (cc & ~(uint32_t)(NPX - 1)) + pair_off<NPX, 8>(cc & (NPX - 1));
+        }
+        float acc = 0.f;
+        uint32_t row = row_new, w = w25;
+#pragma unroll 1
+        for (int ky = 0; ky < 5; ky++) {
+            row += kRowB;                       // oldest row first: the slot after the newest
+            if (row >= ring_end) row = ring_warp;
+#pragma unroll
+            for (int kx = 0; kx < 5; kx++) acc = __fadd_rn(acc, __fmul_rn((float)lds_u32(row + col[kx]), lds_f32(w + 4 * kx)));
+            w += 20;
+        }
+        sts_u32(a, __float_as_uint(kBias + truncf(fminf(fmaxf(acc, 0.f), 255.f))));
     }
-    float acc = 0.f;
-    int slot = slot_new;
-#pragma unroll
-    for (int ky = 0; ky < 5; ky++) {
-        slot = slot == 4 ? 0 : slot + 1;  // oldest row first
-        const uint32_t row = (uint32_t)slot * (32 * NPX * 4);
-#pragma unroll
-        for (int kx = 0; kx < 5; kx++) acc = __fadd_rn(acc, __fmul_rn((float)lds_u32(col[kx] + row), lds_f32(w25 + 4 * (ky * 5 + kx))));
-    }
-    return kBias + truncf(fminf(fmaxf(acc, 0.f), 255.f));
+    if (slow_counter && n) atomicAdd(slow_counter, (unsigned long long)n);
 }
 
 // One image row of the sliding window: consumes the input row held in `buf` (row r, clamped to the
@@ -262,13 +280,14 @@ __device__ __noinline__ float blur_exact_one(uint32_t ring_warp, int c, int cmin
 // row r - HALO.  The border rules are applied at run time (per-lane selects in x, two rare uniform
 // branches in y), so this is the only copy of the row body; the caller unrolls it by three with three
 // row buffers, which makes the buffer rotation and the two-row Sobel delay line register renames.
-template <int NPX, int CN, bool BGR, bool BLUR>
+template <int NPX, int CN, bool BGR, bool BLUR, bool SPECIAL>
 __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, const X2Params &xp, GeoX &geo, int r)
 {
     constexpr int NP = NPX / 2;
     constexpr int kRowB = 32 * NPX * 4;  // bytes per ring row
     const FusedParams &p = xp.f;
     const int W = p.W, H = p.H;
+    (void)H;
 
     // ---- 1. gray of row r; refill the buffer with row r + 3 ---------------------------------------
     u64 Q[NP];
@@ -285,13 +304,18 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
             for (int j = 0; j < NP; j++) sts_b64(pairs + 8 * j, Q[j]);
         }
         if (__builtin_expect(__any_sync(FULL, flagged), 0)) {
-            if constexpr (!BLUR) {
+            if (flagged) {
+                if constexpr (!BLUR) {
 #pragma unroll
-                for (int j = 0; j < NP; j++) sts_b64(pairs + 8 * j, Q[j]);
+                    for (int j = 0; j < NP; j++) sts_b64(pairs + 16 * j, Q[j]);
+                }
+                constexpr int NW = NPX * CN / 4;
+#pragma unroll
+                for (int k = 0; k < NW; k++) sts_u32(geo.patch + 8 * NPX + 4 * k, buf.w[k]);
+                gray_patch<NPX, CN, BGR, BLUR ? 8 : 16>(gray_flag_mask<NPX>(E), pairs, geo.patch + 8 * NPX);
             }
-            gray_patch_call<NPX, CN, BGR>(gray_flag_mask<NPX>(E), pairs, buf.w);
         }
-        reload_pairs_if<NP>(Q, pairs, flagged);
+        reload_pairs_if<NP, BLUR ? 8 : 16>(Q, pairs, flagged);
         if ((unsigned)(r - geo.adv_lo) < (unsigned)geo.adv_n) geo.src += geo.in_pitch;
         load_row_x2<NPX, CN>(buf, geo.src);
     }
@@ -343,26 +367,14 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
             zmin = __vimin3_u32(zmin, (lo2u(F[j]) << (32 - kFracBits)) + xp.zoff, (hi2u(F[j]) << (32 - kFracBits)) + xp.zoff);
         const uint32_t flagged = zmin < xp.zthr ? 1u : 0u;
         if (__builtin_expect(__any_sync(FULL, flagged), 0)) {
-            uint32_t mask = 0;
 #pragma unroll
-            for (int j = 0; j < NP; j++) {
-                mask |= (((lo2u(F[j]) << (32 - kFracBits)) + xp.zoff) < xp.zthr ? 1u : 0u) << j;
-                mask |= (((hi2u(F[j]) << (32 - kFracBits)) + xp.zoff) < xp.zthr ? 1u : 0u) << (j + NP);
-            }
-            if (p.slow_counter && mask) atomicAdd(p.slow_counter, (unsigned long long)__popc(mask));
-            const int slot = (int)((geo.ring_cur - geo.ring_warp) / kRowB);
-#pragma unroll
-            for (int j = 0; j < NP; j++) sts_b64(geo.patch + 8 * j, F[j]);
+            for (int j = 0; j < NP; j++) sts_b64(geo.patch + 16 * j, F[j]);
             __syncwarp();  // the newest ring row was just stored by the other lanes
-            while (mask) {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float v = blur_exact_one<NPX>(geo.ring_warp, NPX * geo.lane + j, geo.cmin, geo.cmax, slot, geo.w25);
-                sts_u32(geo.patch + 4u * (uint32_t)(2 * (j % NP) + j / NP), __float_as_uint(v));
-            }
+            if (flagged)
+                blur_replay_lane<NPX>(geo.patch, geo.ring_warp, geo.ring_cur, geo.w25, geo.cmin, geo.cmax, xp.zoff, xp.zthr, p.slow_counter);
             __syncwarp();  // the ring slot of the oldest row is overwritten by the next step
         }
-        reload_pairs_if<NP>(F, geo.patch, flagged);
+        reload_pairs_if<NP, 16>(F, geo.patch, flagged);
 #pragma unroll
         for (int j = 0; j < NP; j++) F[j] = pk2u(lo2u(F[j]) & kBiasMask, hi2u(F[j]) & kBiasMask);   // kBias + floor(S)
     } else {
@@ -374,17 +386,17 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
 
     // ---- 3. Sobel, vertical pass first: output row yo = yb-1 reads rows yb-2, yb-1, yb -------------
     // BORDER_REFLECT_101 in y: row -1 -> row 1 (first output row), row H -> row H-2 (last output row;
-    // this step's input row is a dummy then).  The empty volatile asm keeps these two rare, warp-uniform
-    // cases real branches instead of 2*NPX selects per row.
-    if (__builtin_expect(yb == 1, 0)) {
-        asm volatile("" ::: "memory");
+    // this step's input row is a dummy then).  Only the SPECIAL copy of the row body carries these
+    // checks; the caller runs it for the first and last trips of a segment only.
+    if constexpr (SPECIAL) {
+        if (yb == 1) {
 #pragma unroll
-        for (int j = 0; j < NP; j++) st.F2[j] = F[j];
-    }
-    if (__builtin_expect(yb == H, 0)) {
-        asm volatile("" ::: "memory");
+            for (int j = 0; j < NP; j++) st.F2[j] = F[j];
+        }
+        if (yb == H) {
 #pragma unroll
-        for (int j = 0; j < NP; j++) F[j] = st.F2[j];
+            for (int j = 0; j < NP; j++) F[j] = st.F2[j];
+        }
     }
     const u64 TWO = pk2(2.f, 2.f);
     u64 Vs[NP], Vd[NP];   // Vs = f(yb-2) + 2 f(yb-1) + f(yb),  Vd = f(yb) - f(yb-2)
@@ -451,7 +463,7 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     const FusedParams &p = xp.f;
 
     __shared__ __align__(16) uint32_t ring[BLUR ? kWarpsPerBlock * 5 * kRowW : 4];
-    __shared__ __align__(16) uint32_t patch[kWarpsPerBlock * kRowW];
+    __shared__ __align__(16) uint32_t patch[kWarpsPerBlock * 3 * kRowW];   // per lane: NPX/2 pairs at a 16-byte stride + NPX words of raw input
     __shared__ float w25s[32];
     if (threadIdx.x < 25) w25s[threadIdx.x] = p.w[threadIdx.x];
     __syncthreads();  // the only block-level barrier: the warps are independent from here on
@@ -461,7 +473,7 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     const int warp = threadIdx.x >> 5;
     geo.ring_warp = (uint32_t)__cvta_generic_to_shared(ring + (BLUR ? warp * 5 * kRowW : 0));
     geo.ring_cur = geo.ring_warp + NPX * 4 * geo.lane;
-    geo.patch = (uint32_t)__cvta_generic_to_shared(patch + threadIdx.x * NPX);
+    geo.patch = (uint32_t)__cvta_generic_to_shared(patch + threadIdx.x * 3 * NPX);
     geo.w25 = (uint32_t)__cvta_generic_to_shared(w25s);
     int bid = blockIdx.x;
     const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
@@ -511,11 +523,25 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     // output row produced by the step of input row r is r - HALO
     geo.dst = p.out + (size_t)frame * p.out_rows * W + (ptrdiff_t)(r - HALO - p.out_row0) * W + x;
 
-    // three rows per trip; up to two trailing steps past r_last compute nothing that is stored
+    // Head: the warm-up rows and the first storing row (it may be frame row 0), one row per trip with
+    // the SPECIAL copy of the row body and an explicit rotation of the three row buffers.  Main loop:
+    // three rows per trip with the plain copy; the buffer rotation and the Sobel delay line are register
+    // renames there.  Tail: the remaining one to three rows (the last may be frame row H-1), SPECIAL again.
+    // Only the main loop is hot, so only its three copies of the row body need to stay in the instruction cache.
 #pragma unroll 1
-    for (; r <= geo.r_last; r += 3) {
-        step_x2<NPX, CN, BGR, BLUR>(st, b0, xp, geo, r);
-        step_x2<NPX, CN, BGR, BLUR>(st, b1, xp, geo, r + 1);
-        step_x2<NPX, CN, BGR, BLUR>(st, b2, xp, geo, r + 2);
+    for (; r <= geo.r_store && r < geo.r_last; r++) {
+        step_x2<NPX, CN, BGR, BLUR, true>(st, b0, xp, geo, r);
+        const RawX<NPX, CN> t = b0; b0 = b1; b1 = b2; b2 = t;
+    }
+#pragma unroll 1
+    for (; r + 3 <= geo.r_last; r += 3) {
+        step_x2<NPX, CN, BGR, BLUR, false>(st, b0, xp, geo, r);
+        step_x2<NPX, CN, BGR, BLUR, false>(st, b1, xp, geo, r + 1);
+        step_x2<NPX, CN, BGR, BLUR, false>(st, b2, xp, geo, r + 2);
+    }
+#pragma unroll 1
+    for (; r <= geo.r_last; r++) {
+        step_x2<NPX, CN, BGR, BLUR, true>(st, b0, xp, geo, r);
+        const RawX<NPX, CN> t = b0; b0 = b1; b1 = b2; b2 = t;
     }
 }
