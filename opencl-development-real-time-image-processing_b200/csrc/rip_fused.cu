@@ -802,6 +802,9 @@ static bool plan_weights_band(const float *w25, float g[3], double *band_out)
     double sum = 0.0;
     for (int i = 0; i < 25; i++) {
         if (!(w25[i] >= 0.0f) || !std::isfinite(w25[i])) return false;
+        // the x2 kernel feeds gray in as q * 2^-149 and carries the 2^149 in the weights; a product must
+        // stay a normal float for its rounding to equal the reference's (rip_fused_x2.cuh)
+        if (w25[i] != 0.0f && w25[i] < 8.470329472543003e-22f /* 2^-70 */) return false;
         sum += (double)w25[i];
     }
     if (!(sum > 0.0) || 255.0 * sum >= 255.9) return false;  // floor(S) must stay <= 255

@@ -223,7 +223,8 @@ struct GeoX {
                              // within a lane's NPX words the pixels sit in pair order, see reload_pairs_if)
     uint32_t ring_cur;       // byte address of this lane's words in the ring row holding the newest gray row
     uint32_t patch;          // byte address of this lane's NPX words of scratch for the cold paths
-    uint32_t w25;            // shared-memory byte address of the exact 2-D weights (for the replay)
+    uint32_t w25;            // shared-memory byte address of the exact 2-D weights times 2^100 (for the replay)
+    uint32_t scratch;        // shared-memory byte address of this warp's 32-float scratch row (for the replay)
     uint32_t in_pitch;
     int adv_lo, adv_n;       // the source pointer advances before the load of step r iff 0 <= r - adv_lo < adv_n
     int lane;
@@ -233,46 +234,67 @@ struct GeoX {
     int r_store, r_last;     // first / last step that produces an output row
 };
 
-// Cold (inline, see gray_patch): exact replay for the pixels of one lane that sit inside the guard band.
-// `patch` holds a copy of the lane's NPX biased sums S~ + kBias (pair order); every pixel whose fraction
-// bits are within the band is replaced there by kBias + floor(reference sum): the reference's 25-tap sum
-// (GaussianBlur.cpp:236-258), ky-major / kx-minor from 0.0f, unfused multiply and add, clamp, truncate,
-// read from the warp's gray ring.  Columns are clamped to [cmin, cmax] (clamp-to-edge, GaussianBlur.cpp:240).
-// Kept small (row loop rolled) because three copies of it sit inside the hot loop's address range.
+// Cold (inline, see gray_patch): exact replay of the pixels inside the guard band, warp-cooperatively.
+// The whole warp is held up by one flagged pixel anyway, so all of it works on that pixel: lane t < 25
+// fetches tap t (ky = t / 5, kx = t % 5) of the pixel's 5x5 gray window from the warp's ring and forms
+// the reference's rounded product; the products go through a 32-float scratch row to the pixel's owner
+// lane, which adds them in the reference's order (GaussianBlur.cpp:236-258: ky-major / kx-minor from 0.0f,
+// unfused), clamps, truncates and writes kBias + b over its copy of the pixel in `patch`.
+// The ring holds gray as integer bit patterns (= q * 2^-149 as floats) and `w25` the weights times 2^100:
+// fl(q*2^-149 * w*2^100) = fl(q * w) * 2^-49 exactly (same mantissa, results stay normal), likewise every
+// partial sum, so the scaled chain rounds exactly like the reference's and needs no integer-to-float
+// conversion.  Columns are clamped to [cmin, cmax] (clamp-to-edge, GaussianBlur.cpp:240).
 template <int NPX>
-__device__ __forceinline__ void blur_replay_lane(uint32_t patch, uint32_t ring_warp, uint32_t ring_cur, uint32_t w25, int cmin, int cmax,
-                                                 uint32_t zoff, uint32_t zthr, unsigned long long *slow_counter)
+__device__ __forceinline__ void blur_replay_warp(const u64 *F, uint32_t patch, uint32_t scratch, uint32_t ring_warp, uint32_t ring_cur,
+                                                 uint32_t w25, int cmin, int cmax, uint32_t zoff, uint32_t zthr,
+                                                 unsigned long long *slow_counter)
 {
+    constexpr int NP = NPX / 2;
     constexpr uint32_t kRowB = 32 * NPX * 4;
-    const int lane = threadIdx.x & 31;
-    const uint32_t ring_end = ring_warp + 5 * kRowB;
-    const uint32_t row_new = ring_warp + ((ring_cur - ring_warp) / kRowB) * kRowB;   // start of the newest ring row
-    int n = 0;
-#pragma unroll 1
-    for (uint32_t j = 0; j < NPX; j++) {
-        const uint32_t a = patch + pair_off<NPX, 16>(j);
-        if (((lds_u32(a) << (32 - kFracBits)) + zoff) >= zthr) continue;
-        n++;
-        const int c = NPX * lane + (int)j;
-        uint32_t col[5];   // byte offset of columns x-2 .. x+2 inside a ring row
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t my = 0;   // this lane's pixels inside the guard band (bit j = pixel j)
 #pragma unroll
-        for (int kx = 0; kx < 5; kx++) {
-            const uint32_t cc = (uint32_t)min(max(c + kx - 2, cmin), cmax);
-            col[kx] = 4u * (cc & ~(uint32_t)(NPX - 1)) + pair_off<NPX, 8>(cc & (NPX - 1));
-        }
-        float acc = 0.f;
-        uint32_t row = row_new, w = w25;
-#pragma unroll 1
-        for (int ky = 0; ky < 5; ky++) {
-            row += kRowB;                       // oldest row first: the slot after the newest
-            if (row >= ring_end) row = ring_warp;
-#pragma unroll
-            for (int kx = 0; kx < 5; kx++) acc = __fadd_rn(acc, __fmul_rn((float)lds_u32(row + col[kx]), lds_f32(w + 4 * kx)));
-            w += 20;
-        }
-        sts_u32(a, __float_as_uint(kBias + truncf(fminf(fmaxf(acc, 0.f), 255.f))));
+    for (int j = 0; j < NP; j++) {
+        my |= (((lo2u(F[j]) << (32 - kFracBits)) + zoff) < zthr ? 1u : 0u) << j;
+        my |= (((hi2u(F[j]) << (32 - kFracBits)) + zoff) < zthr ? 1u : 0u) << (j + NP);
     }
-    if (slow_counter && n) atomicAdd(slow_counter, (unsigned long long)n);
+    uint32_t lanes = __ballot_sync(FULL, my != 0u);
+    // this lane's tap: ring row of ky (oldest row first: the slot after the newest), column offset, weight
+    const uint32_t t = lane < 25u ? lane : 24u, ky = t / 5u, kx = t - 5u * ky;
+    uint32_t slot = (ring_cur - ring_warp) / kRowB + 1u + ky;
+    slot = slot >= 5u ? slot - 5u : slot;
+    const uint32_t row = ring_warp + slot * kRowB;
+    const float wt = lds_f32(w25 + 4u * t);
+    const int dx = (int)kx - 2;
+#pragma unroll 1
+    while (lanes) {
+        const uint32_t src = (uint32_t)__ffs(lanes) - 1u;
+        lanes &= lanes - 1u;
+        uint32_t m = __shfl_sync(FULL, my, src);
+#pragma unroll 1
+        while (m) {
+            const uint32_t j = (uint32_t)__ffs(m) - 1u;
+            m &= m - 1u;
+            const uint32_t cc = (uint32_t)min(max((int)(NPX * src + j) + dx, cmin), cmax);
+            const uint32_t g = lds_u32(row + 4u * (cc & ~(uint32_t)(NPX - 1)) + pair_off<NPX, 8>(cc & (NPX - 1)));
+            sts_u32(scratch + 4u * lane, __float_as_uint(__fmul_rn(__uint_as_float(g), wt)));
+            __syncwarp();
+            if (lane == src) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 24; k += 4) {
+                    float p0, p1, p2, p3;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p0), "=f"(p1), "=f"(p2), "=f"(p3) : "r"(scratch + 4 * k));
+                    acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, p0), p1), p2), p3);
+                }
+                acc = __fadd_rn(acc, lds_f32(scratch + 4 * 24));
+                acc = __fmul_rn(acc, 562949953421312.0f);   // * 2^49: back to the reference's scale (exact)
+                sts_u32(patch + pair_off<NPX, 16>(j), __float_as_uint(kBias + truncf(fminf(fmaxf(acc, 0.f), 255.f))));
+                if (slow_counter) atomicAdd(slow_counter, 1ull);
+            }
+            __syncwarp();
+        }
+    }
 }
 
 // One image row of the sliding window: consumes the input row held in `buf` (row r, clamped to the
@@ -303,6 +325,7 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
 #pragma unroll
             for (int j = 0; j < NP; j++) sts_b64(pairs + 8 * j, Q[j]);
         }
+#ifndef RIP_X2_NOCOLD   // (experiment switch: hot path only, wrong results)
         if (__builtin_expect(__any_sync(FULL, flagged), 0)) {
             if (flagged) {
                 if constexpr (!BLUR) {
@@ -316,6 +339,7 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
             }
         }
         reload_pairs_if<NP, BLUR ? 8 : 16>(Q, pairs, flagged);
+#endif
         if ((unsigned)(r - geo.adv_lo) < (unsigned)geo.adv_n) geo.src += geo.in_pitch;
         load_row_x2<NPX, CN>(buf, geo.src);
     }
@@ -366,15 +390,19 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
         for (int j = 0; j < NP; j++)
             zmin = __vimin3_u32(zmin, (lo2u(F[j]) << (32 - kFracBits)) + xp.zoff, (hi2u(F[j]) << (32 - kFracBits)) + xp.zoff);
         const uint32_t flagged = zmin < xp.zthr ? 1u : 0u;
+#ifndef RIP_X2_NOCOLD
         if (__builtin_expect(__any_sync(FULL, flagged), 0)) {
 #pragma unroll
             for (int j = 0; j < NP; j++) sts_b64(geo.patch + 16 * j, F[j]);
             __syncwarp();  // the newest ring row was just stored by the other lanes
-            if (flagged)
-                blur_replay_lane<NPX>(geo.patch, geo.ring_warp, geo.ring_cur, geo.w25, geo.cmin, geo.cmax, xp.zoff, xp.zthr, p.slow_counter);
-            __syncwarp();  // the ring slot of the oldest row is overwritten by the next step
+            blur_replay_warp<NPX>(F, geo.patch, geo.scratch, geo.ring_warp, geo.ring_cur, geo.w25, geo.cmin, geo.cmax, xp.zoff, xp.zthr,
+                                  p.slow_counter);
+            // (its trailing __syncwarp also orders the ring reads before the next step overwrites the oldest slot)
         }
         reload_pairs_if<NP, 16>(F, geo.patch, flagged);
+#else
+        if (flagged == 77u) F[0] = 0;
+#endif
 #pragma unroll
         for (int j = 0; j < NP; j++) F[j] = pk2u(lo2u(F[j]) & kBiasMask, hi2u(F[j]) & kBiasMask);   // kBias + floor(S)
     } else {
@@ -465,7 +493,8 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     __shared__ __align__(16) uint32_t ring[BLUR ? kWarpsPerBlock * 5 * kRowW : 4];
     __shared__ __align__(16) uint32_t patch[kWarpsPerBlock * 3 * kRowW];   // per lane: NPX/2 pairs at a 16-byte stride + NPX words of raw input
     __shared__ float w25s[32];
-    if (threadIdx.x < 25) w25s[threadIdx.x] = p.w[threadIdx.x];
+    __shared__ __align__(16) float scratch[kWarpsPerBlock * 32];
+    if (threadIdx.x < 25) w25s[threadIdx.x] = p.w[threadIdx.x] * 1.2676506002282294e30f;   // * 2^100 (exact), see blur_replay_warp
     __syncthreads();  // the only block-level barrier: the warps are independent from here on
 
     GeoX geo;
@@ -475,6 +504,7 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     geo.ring_cur = geo.ring_warp + NPX * 4 * geo.lane;
     geo.patch = (uint32_t)__cvta_generic_to_shared(patch + threadIdx.x * 3 * NPX);
     geo.w25 = (uint32_t)__cvta_generic_to_shared(w25s);
+    geo.scratch = (uint32_t)__cvta_generic_to_shared(scratch + 32 * (threadIdx.x >> 5));
     int bid = blockIdx.x;
     const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
     const int seg = bid % p.n_segs;
