@@ -51,6 +51,9 @@
 #ifndef RIP_X2_UNROLL
 #define RIP_X2_UNROLL 3
 #endif
+#ifndef RIP_X2_L2PF
+#define RIP_X2_L2PF 6   // rows ahead of the register loads that prefetch.global.L2 runs (0 = off)
+#endif
 
 namespace rip {
 
@@ -842,9 +845,10 @@ static int pick_seg_rows(int out_rows, int n_frames, int n_band_groups, int devi
         const int v = atoi(e);
         if (v > 0) return v < out_rows ? v : out_rows;
     }
-    // enough blocks for >= ~8 waves of (SMs x 6 resident blocks), but segments of >= 64 rows so the
-    // 6 warm-up rows stay below 10 %; never more than 256 rows (tail balance).
-    const long long target_blocks = (long long)sm_count(device) * resident_blocks * 8;
+    // enough blocks for >= ~3 waves of (SMs x resident blocks), but segments of >= 64 rows so the
+    // 6 warm-up rows stay below 10 %; never more than 256 rows (tail balance).  (Measured on 32 4K
+    // frames: 64 rows 440 us, 128 rows 416 us, 270 rows 415 us.)
+    const long long target_blocks = (long long)sm_count(device) * resident_blocks * 3;
     int seg = 256;
     while (seg > 64 && (long long)n_frames * n_band_groups * ((out_rows + seg - 1) / seg) < target_blocks) seg >>= 1;
     if (seg > out_rows) seg = out_rows;
@@ -1163,6 +1167,10 @@ template <int NPX, int CN, bool BGR>
 __global__ void selftest_gray_x2_kernel(unsigned long long *bad)
 {
     constexpr int NP = NPX / 2, NW = NPX * CN / 4;
+    __shared__ uint32_t table[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) table[i] = d_gray_down[i];
+    __syncthreads();
+    const uint32_t table_s = (uint32_t)__cvta_generic_to_shared(table);
     // thread q handles triples NPX*q .. NPX*q + NPX-1 (triple i: c0 = i & 255, c1 = (i >> 8) & 255, c2 = i >> 16)
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < (1u << 24) / NPX; q += gridDim.x * blockDim.x) {
         uint8_t bytes[NW * 4];
@@ -1178,7 +1186,7 @@ __global__ void selftest_gray_x2_kernel(unsigned long long *bad)
             w[k] = bytes[4 * k] | (bytes[4 * k + 1] << 8) | (bytes[4 * k + 2] << 16) | ((uint32_t)bytes[4 * k + 3] << 24);
         u64 Q[NP], E[NP];
         const uint32_t any = gray_x2<NPX, CN, BGR>(w, Q, E);
-        if (any & 1u) gray_fix_x2<NPX, CN, BGR>(w, Q, E);
+        if (any & 1u) gray_fix_x2<NPX, CN, BGR>(w, Q, E, table_s);
 #pragma unroll
         for (int j = 0; j < NPX; j++) {
             const unsigned i = NPX * q + j;

@@ -139,7 +139,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) { uint32_t v; asm vola
 // decrement the copy of that pixel's gray at `pairs`.  `raw` is a shared-memory copy of the lane's
 // input bytes, so a run-time pixel index needs no select chains.
 template <int NPX, int CN, bool BGR, int STRIDE>
-__device__ __forceinline__ void gray_patch(uint32_t m, uint32_t pairs, uint32_t raw)
+__device__ __forceinline__ void gray_patch(uint32_t m, uint32_t pairs, uint32_t raw, uint32_t table /* d_gray_down staged in shared memory */)
 {
 #pragma unroll 1
     while (m) {
@@ -147,7 +147,7 @@ __device__ __forceinline__ void gray_patch(uint32_t m, uint32_t pairs, uint32_t 
         m &= m - 1;
         const uint32_t r = lds_u8(raw + CN * j + (BGR ? 2 : 0)), g = lds_u8(raw + CN * j + 1);
         const uint32_t idx = (r << 8) | g;
-        const uint32_t down = (__ldg(&d_gray_down[idx >> 5]) >> (idx & 31u)) & 1u;
+        const uint32_t down = (lds_u32(table + 4u * (idx >> 5)) >> (idx & 31u)) & 1u;
         const uint32_t a = pairs + pair_off<NPX, STRIDE>(j);
         sts_u32(a, lds_u32(a) - down);
     }
@@ -166,9 +166,10 @@ __device__ __forceinline__ uint32_t gray_flag_mask(const u64 *E)
     return m & ((1u << NPX) - 1u);
 }
 
-// register-in / register-out variant for the self-test (not used by the kernel)
+// register-in / register-out variant for the self-test (not used by the kernel); `table` = shared-memory
+// address of a staged copy of d_gray_down
 template <int NPX, int CN, bool BGR>
-__device__ __forceinline__ void gray_fix_x2(const uint32_t *w, u64 *Q, const u64 *E)
+__device__ __forceinline__ void gray_fix_x2(const uint32_t *w, u64 *Q, const u64 *E, uint32_t table)
 {
     constexpr int NP = NPX / 2, NW = NPX * CN / 4;
     __shared__ __align__(16) uint32_t scratch[256 * 3 * NPX];
@@ -177,7 +178,7 @@ __device__ __forceinline__ void gray_fix_x2(const uint32_t *w, u64 *Q, const u64
     for (int j = 0; j < NP; j++) sts_b64(pairs + 16 * j, Q[j]);
 #pragma unroll
     for (int k = 0; k < NW; k++) sts_u32(raw + 4 * k, w[k]);
-    gray_patch<NPX, CN, BGR, 16>(gray_flag_mask<NPX>(E), pairs, raw);
+    gray_patch<NPX, CN, BGR, 16>(gray_flag_mask<NPX>(E), pairs, raw, table);
     reload_pairs_if<NP, 16>(Q, pairs, 1u);
 }
 
@@ -225,8 +226,10 @@ struct GeoX {
     uint32_t patch;          // byte address of this lane's NPX words of scratch for the cold paths
     uint32_t w25;            // shared-memory byte address of the exact 2-D weights times 2^100 (for the replay)
     uint32_t scratch;        // shared-memory byte address of this warp's 32-float scratch row (for the replay)
+    uint32_t table;          // shared-memory byte address of the block's copy of d_gray_down
     uint32_t in_pitch;
     int adv_lo, adv_n;       // the source pointer advances before the load of step r iff 0 <= r - adv_lo < adv_n
+    uint32_t pf_off;         // byte offset from src of the line this lane prefetches into L2 (0: none)
     int lane;
     int cmin, cmax;          // first / last column of the band (0 = pixel 0 of lane 0) that lies inside the image
     bool e_left, e_right;    // this lane holds image column 0 / W-1 (border rules in x apply to it)
@@ -335,13 +338,19 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
                 constexpr int NW = NPX * CN / 4;
 #pragma unroll
                 for (int k = 0; k < NW; k++) sts_u32(geo.patch + 8 * NPX + 4 * k, buf.w[k]);
-                gray_patch<NPX, CN, BGR, BLUR ? 8 : 16>(gray_flag_mask<NPX>(E), pairs, geo.patch + 8 * NPX);
+                gray_patch<NPX, CN, BGR, BLUR ? 8 : 16>(gray_flag_mask<NPX>(E), pairs, geo.patch + 8 * NPX, geo.table);
             }
+            reload_pairs_if<NP, BLUR ? 8 : 16>(Q, pairs, flagged);
         }
-        reload_pairs_if<NP, BLUR ? 8 : 16>(Q, pairs, flagged);
 #endif
         if ((unsigned)(r - geo.adv_lo) < (unsigned)geo.adv_n) geo.src += geo.in_pitch;
         load_row_x2<NPX, CN>(buf, geo.src);
+#if RIP_X2_L2PF > 0
+        // pull the warp's bytes of a row further down into L2 (one 128-byte line per lane; pf_off is 0 in
+        // the lanes that have no line to fetch and at the rows the band does not hold)
+        if (geo.pf_off != 0 && (unsigned)(r - geo.adv_lo) + RIP_X2_L2PF < (unsigned)geo.adv_n)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(geo.src + geo.pf_off));
+#endif
     }
 
     // F[j] = (f[j], f[j + NP]): the row the Sobel stage consumes (blurred row yb, biased by kBias, or
@@ -398,8 +407,8 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
             blur_replay_warp<NPX>(F, geo.patch, geo.scratch, geo.ring_warp, geo.ring_cur, geo.w25, geo.cmin, geo.cmax, xp.zoff, xp.zthr,
                                   p.slow_counter);
             // (its trailing __syncwarp also orders the ring reads before the next step overwrites the oldest slot)
+            reload_pairs_if<NP, 16>(F, geo.patch, flagged);
         }
-        reload_pairs_if<NP, 16>(F, geo.patch, flagged);
 #else
         if (flagged == 77u) F[0] = 0;
 #endif
@@ -494,6 +503,8 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     __shared__ __align__(16) uint32_t patch[kWarpsPerBlock * 3 * kRowW];   // per lane: NPX/2 pairs at a 16-byte stride + NPX words of raw input
     __shared__ float w25s[32];
     __shared__ __align__(16) float scratch[kWarpsPerBlock * 32];
+    __shared__ uint32_t gray_down_s[2048];   // the (r,g) bit table of the gray fix: global-memory latency would stall the whole warp
+    for (int i = threadIdx.x; i < 2048; i += kWarpsPerBlock * 32) gray_down_s[i] = d_gray_down[i];
     if (threadIdx.x < 25) w25s[threadIdx.x] = p.w[threadIdx.x] * 1.2676506002282294e30f;   // * 2^100 (exact), see blur_replay_warp
     __syncthreads();  // the only block-level barrier: the warps are independent from here on
 
@@ -505,6 +516,7 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     geo.patch = (uint32_t)__cvta_generic_to_shared(patch + threadIdx.x * 3 * NPX);
     geo.w25 = (uint32_t)__cvta_generic_to_shared(w25s);
     geo.scratch = (uint32_t)__cvta_generic_to_shared(scratch + 32 * (threadIdx.x >> 5));
+    geo.table = (uint32_t)__cvta_generic_to_shared(gray_down_s);
     int bid = blockIdx.x;
     const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
     const int seg = bid % p.n_segs;
@@ -550,6 +562,12 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     // step r loads row r + 3 = one past the row src points at: advance iff in_row0 <= r + 2 < in_row0 + in_rows - 1
     geo.adv_lo = p.in_row0 - 2;
     geo.adv_n = p.in_rows - 1;
+    {   // lanes 0..n-1 fetch the n consecutive 128-byte lines that hold the warp's NPX*CN*32 bytes of a row
+        constexpr int kLines = (32 * NPX * CN + 127) / 128 + 1;
+        const uint32_t lane0_to_me = (uint32_t)(NPX * CN) * (uint32_t)geo.lane;   // src points at this lane's pixels
+        geo.pf_off = (in_img && geo.lane < kLines) ? (uint32_t)RIP_X2_L2PF * geo.in_pitch + 128u * (uint32_t)geo.lane - lane0_to_me : 0u;
+        if (x - NPX * geo.lane < 0) geo.pf_off = 0u;   // (left-most band: lane 0 sits before the row; keep it simple)
+    }
     // output row produced by the step of input row r is r - HALO
     geo.dst = p.out + (size_t)frame * p.out_rows * W + (ptrdiff_t)(r - HALO - p.out_row0) * W + x;
 
