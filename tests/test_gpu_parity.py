@@ -134,9 +134,9 @@ def test_sobel_gray_input_matches_opencv_goldens(ctx, golden_cv2_sobel, golden_i
 
 @pytest.mark.parametrize("shape", [(2, 4), (2, 8), (5, 12), (37, 120), (37, 124), (64, 128), (33, 244), (75, 75), (19, 241),
                                    (2, 16), (31, 240), (17, 256), (40, 496)])
-@pytest.mark.parametrize("fmt,cn,tma", [(rip.FMT_RGB8, 3, 0), (rip.FMT_RGBA8, 4, 0), (rip.FMT_BGR8, 3, 0), (rip.FMT_RGB8, 3, 1), (rip.FMT_RGBA8, 4, 1)])
-def test_sobel_colour_input(ctx, oracle, shape, fmt, cn, tma, monkeypatch):
-    monkeypatch.setenv("RIP_FUSED_TMA", str(tma))
+@pytest.mark.parametrize("fmt,cn,npx", [(rip.FMT_RGB8, 3, 8), (rip.FMT_RGBA8, 4, 8), (rip.FMT_BGR8, 3, 8), (rip.FMT_RGB8, 3, 4), (rip.FMT_RGBA8, 4, 4)])
+def test_sobel_colour_input(ctx, oracle, shape, fmt, cn, npx, monkeypatch):
+    monkeypatch.setenv("RIP_FUSED_NPX", str(npx))  # pixels per lane of the fused kernel (8 where the width allows it)
     img = synth_frame("uniform", shape[0], shape[1], 21, cn)
     g = oracle.gray(img, oracle.BGR if fmt == rip.FMT_BGR8 else oracle.RGB)
     _eq(ctx.process(img, rip.OP_EDGE, fmt), oracle.sobel(g), f"sobel colour {shape} cn={cn}")
@@ -155,15 +155,15 @@ def test_sobel_config3_1080p_batch(ctx, oracle):
 
 
 # ---- fused gray -> blur -> Sobel (configs 4, 5) ------------------------------------------------
-# widths with W*3 % 16 == 0 take the TMA kernel (8-pixel lanes), other multiples of 4 the LDG kernel
+# widths that are multiples of 8 run 8 pixels per lane, other multiples of 4 run 4 (RIP_FUSED_NPX=4 forces 4)
 FUSED_SHAPES = [(2, 4), (3, 8), (7, 12), (16, 120), (40, 124), (9, 128), (70, 244), (130, 364), (300, 480), (64, 1920),
                 (2, 16), (5, 16), (9, 32), (41, 240), (33, 256), (64, 496), (23, 272), (300, 16)]
 
 
 @pytest.mark.parametrize("shape", FUSED_SHAPES)
-@pytest.mark.parametrize("kind,tma", [("uniform", 0), ("smooth", 0), ("uniform", 1)])
-def test_fused_single_kernel_path(ctx, oracle, shape, kind, tma, monkeypatch):
-    monkeypatch.setenv("RIP_FUSED_TMA", str(tma))  # 1: TMA-staged kernel where the shape allows it
+@pytest.mark.parametrize("kind,npx", [("uniform", 8), ("smooth", 8), ("uniform", 4)])
+def test_fused_single_kernel_path(ctx, oracle, shape, kind, npx, monkeypatch):
+    monkeypatch.setenv("RIP_FUSED_NPX", str(npx))
     img = synth_frame(kind, shape[0], shape[1], 31)
     w = rip.gauss_weights(5, 1.0)
     _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w, threads=0),
@@ -171,9 +171,9 @@ def test_fused_single_kernel_path(ctx, oracle, shape, kind, tma, monkeypatch):
 
 
 @pytest.mark.parametrize("fmt,cn,order", [(rip.FMT_RGBA8, 4, "RGB"), (rip.FMT_BGR8, 3, "BGR"), (rip.FMT_BGRA8, 4, "BGR")])
-@pytest.mark.parametrize("sigma,tma", [(1.0, 0), (1.5, 0), (1.5, 1)])
-def test_fused_formats_and_sigmas(ctx, oracle, fmt, cn, order, sigma, tma, monkeypatch):
-    monkeypatch.setenv("RIP_FUSED_TMA", str(tma))
+@pytest.mark.parametrize("sigma,npx", [(1.0, 8), (1.5, 8), (1.5, 4)])
+def test_fused_formats_and_sigmas(ctx, oracle, fmt, cn, order, sigma, npx, monkeypatch):
+    monkeypatch.setenv("RIP_FUSED_NPX", str(npx))
     img = synth_frame("smooth", 97, 248, 41, cn)
     w = rip.gauss_weights(5, sigma)
     want = oracle.fused(img, 5, weights=w, order=oracle.BGR if order == "BGR" else oracle.RGB)
@@ -219,8 +219,8 @@ def test_fused_adversarial_frames(ctx, oracle, sigma):
     _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w), "fused colour ramps")
 
 
-def test_fused_ldg_and_tma_kernels_agree(oracle, monkeypatch):
-    """The LDG kernel (fallback for widths TMA cannot address) must match on a TMA-capable shape too."""
+def test_fused_8_and_4_pixel_kernels_agree(oracle, monkeypatch):
+    """The 4-pixels-per-lane kernel (fallback for widths that are not multiples of 8) must match on an 8-capable shape too."""
     h, wd = 120, 496
     img = synth_frame("uniform", h, wd, 77)
     w = rip.gauss_weights(5, 1.0)
@@ -228,13 +228,13 @@ def test_fused_ldg_and_tma_kernels_agree(oracle, monkeypatch):
     d_in = rip.DeviceBuffer(img.nbytes).upload(img)
     d_out = rip.DeviceBuffer(h * wd)
     outs = []
-    for use_tma in (True, False):
-        monkeypatch.setenv("RIP_FUSED_TMA", "1" if use_tma else "0")
+    for npx in (8, 4):
+        monkeypatch.setenv("RIP_FUSED_NPX", str(npx))
         rip.lib().rip_memset_device_async(0, d_out.ptr, 0, h * wd, None)
         rip.fused_dev(d_in.ptr, d_out.ptr, wd, h, 1, rip.FMT_RGB8, 5, w)
         outs.append(d_out.download((h, wd)))
-    _eq(outs[0], want, "TMA kernel")
-    _eq(outs[1], want, "LDG kernel")
+    _eq(outs[0], want, "8 pixels per lane")
+    _eq(outs[1], want, "4 pixels per lane")
 
 
 def test_fused_guard_band_statistics():
@@ -251,9 +251,9 @@ def test_fused_guard_band_statistics():
         assert lo <= frac <= hi, (kind, frac)
 
 
-@pytest.mark.parametrize("wd,tma", [(360, 0), (368, 0), (368, 1)])  # LDG kernel / TMA kernel
-def test_fused_row_bands_equal_whole_frame(ctx, oracle, wd, tma, monkeypatch):
-    monkeypatch.setenv("RIP_FUSED_TMA", str(tma))
+@pytest.mark.parametrize("wd,npx", [(364, 4), (368, 8), (368, 4)])
+def test_fused_row_bands_equal_whole_frame(ctx, oracle, wd, npx, monkeypatch):
+    monkeypatch.setenv("RIP_FUSED_NPX", str(npx))
     h = 200
     img = synth_frame("uniform", h, wd, 81)
     w = rip.gauss_weights(5, 1.0)
