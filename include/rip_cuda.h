@@ -177,6 +177,13 @@ typedef struct rip_op_desc {
 int rip_out_bytes_per_frame(const rip_op_desc *desc, int width, int height, size_t *bytes);
 int rip_process_host(rip_ctx *ctx, const rip_op_desc *desc, const uint8_t *h_in, uint8_t *h_out,
                      int width, int height, int n_frames, uint64_t prof_ns[6]);
+/* The partitions the two host pipelines use (pure host arithmetic, exported so that callers and tests
+ * see exactly the split that runs): part `index` of `n_parts` owns frames [first, first + count) of a
+ * batch, or output rows [out_row0, out_row0 + out_rows) of a frame, for which it needs input rows
+ * [in_row0, in_row0 + in_rows) (halo = ksize/2 + 1 for FUSED, 1 for EDGE; clipped to the image). */
+int rip_shard_frames(int n_frames, int n_parts, int index, int *first, int *count);
+int rip_band_rows(int height, int n_parts, int index, int halo, int *in_row0, int *in_rows,
+                  int *out_row0, int *out_rows);
 /* one large frame split into row bands (one per device of ctx, halo rows replicated from the
  * source frame).  RIP_OP_FUSED and RIP_OP_EDGE only. */
 int rip_process_host_banded(rip_ctx *ctx, const rip_op_desc *desc, const uint8_t *h_in,

@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "rip_memcpy_h2d_async", "rip_memcpy_d2h_async", "rip_memset_device_async",
     "rip_gauss_weights", "rip_gray", "rip_gauss", "rip_sobel", "rip_fused", "rip_fused_workspace_bytes",
     "rip_launch_count", "rip_debug_slow_path_stats", "rip_debug_selftest",
-    "rip_out_bytes_per_frame", "rip_process_host", "rip_process_host_banded",
+    "rip_out_bytes_per_frame", "rip_process_host", "rip_process_host_banded", "rip_shard_frames", "rip_band_rows",
 ]
 
 
@@ -114,6 +114,8 @@ def lib() -> C.CDLL:
         "rip_out_bytes_per_frame": ([C.POINTER(OpDesc), C.c_int, C.c_int, szp], C.c_int),
         "rip_process_host": ([vp, C.POINTER(OpDesc), vp, vp, C.c_int, C.c_int, C.c_int, u64p], C.c_int),
         "rip_process_host_banded": ([vp, C.POINTER(OpDesc), vp, vp, C.c_int, C.c_int, u64p], C.c_int),
+        "rip_shard_frames": ([C.c_int, C.c_int, C.c_int, i32p, i32p], C.c_int),
+        "rip_band_rows": ([C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, i32p], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -159,6 +161,20 @@ def selftest(device: int = 0) -> tuple[int, int]:
     c, m = C.c_uint64(0), C.c_uint64(0)
     check(lib().rip_debug_selftest(device, C.byref(c), C.byref(m)), "rip_debug_selftest")
     return c.value, m.value
+
+
+def shard_frames(n_frames: int, n_parts: int, index: int) -> tuple[int, int]:
+    """(first, count) of the contiguous block of frames part `index` of `n_parts` owns (rip_shard_frames)."""
+    first, count = C.c_int(), C.c_int()
+    check(lib().rip_shard_frames(n_frames, n_parts, index, C.byref(first), C.byref(count)), "rip_shard_frames")
+    return first.value, count.value
+
+
+def band_rows(height: int, n_parts: int, index: int, halo: int) -> tuple[int, int, int, int]:
+    """(in_row0, in_rows, out_row0, out_rows) of row band `index` of `n_parts` (rip_band_rows)."""
+    v = [C.c_int() for _ in range(4)]
+    check(lib().rip_band_rows(height, n_parts, index, halo, *[C.byref(x) for x in v]), "rip_band_rows")
+    return tuple(x.value for x in v)
 
 
 def gauss_weights(ksize: int, sigma: float) -> np.ndarray:

@@ -794,6 +794,27 @@ void fill_prof(uint64_t prof_ns[6], const double ms[3])
 
 }  // namespace
 
+extern "C" int rip_shard_frames(int n_frames, int n_parts, int index, int *first, int *count)
+{
+    if (!first || !count || n_frames < 0 || n_parts <= 0 || index < 0 || index >= n_parts)
+        return fail(RIP_EINVAL, "rip_shard_frames: bad arguments (%d frames, part %d of %d)", n_frames, index, n_parts);
+    const int f0 = (int)((long long)n_frames * index / n_parts), f1 = (int)((long long)n_frames * (index + 1) / n_parts);
+    *first = f0;
+    *count = f1 - f0;
+    return RIP_OK;
+}
+
+extern "C" int rip_band_rows(int height, int n_parts, int index, int halo, int *in_row0, int *in_rows, int *out_row0, int *out_rows)
+{
+    if (!in_row0 || !in_rows || !out_row0 || !out_rows || height <= 0 || n_parts <= 0 || n_parts > height || index < 0 ||
+        index >= n_parts || halo < 0)
+        return fail(RIP_EINVAL, "rip_band_rows: bad arguments (height %d, part %d of %d, halo %d)", height, index, n_parts, halo);
+    const int o0 = (int)((long long)height * index / n_parts), o1 = (int)((long long)height * (index + 1) / n_parts);
+    const int i0 = max(0, o0 - halo), i1 = min(height, o1 + halo);
+    *out_row0 = o0; *out_rows = o1 - o0; *in_row0 = i0; *in_rows = i1 - i0;
+    return RIP_OK;
+}
+
 extern "C" int rip_process_host(rip_ctx *ctx, const rip_op_desc *desc, const uint8_t *h_in, uint8_t *h_out, int width,
                                 int height, int n_frames, uint64_t prof_ns[6])
 {
@@ -822,7 +843,9 @@ extern "C" int rip_process_host(rip_ctx *ctx, const rip_op_desc *desc, const uin
     std::vector<int> rcs(used, RIP_OK);
     std::vector<std::string> errs(used, std::string(512, '\0'));
     for (int i = 0; i < used; i++) {
-        const int f0 = (int)((long long)n_frames * i / used), f1 = (int)((long long)n_frames * (i + 1) / used);
+        int f0 = 0, fc = 0;
+        rip_shard_frames(n_frames, used, i, &f0, &fc);
+        const int f1 = f0 + fc;
         th.emplace_back([&, i, f0, f1]() {
             rcs[i] = run_device(ctx->devs[i], job, h_in, h_out, f0, f1, (i == 0 && prof_ns) ? prof_ms : nullptr, &errs[i][0], errs[i].size());
         });
@@ -858,8 +881,9 @@ extern "C" int rip_process_host_banded(rip_ctx *ctx, const rip_op_desc *desc, co
             int rc = RIP_OK;
             {
                 DeviceGuard g(dev.device);
-                const int o0 = (int)((long long)height * i / nd), o1 = (int)((long long)height * (i + 1) / nd);
-                const int i0 = max(0, o0 - halo), i1 = min(height, o1 + halo);
+                int o0 = 0, on = 0, i0 = 0, in = 0;
+                rip_band_rows(height, nd, i, halo, &i0, &in, &o0, &on);
+                const int o1 = o0 + on, i1 = i0 + in;
                 BufSet &b = dev.set[0];
                 do {
                     if ((rc = ensure(&b.d_in, &b.in_cap, row_in * (i1 - i0)))) break;
