@@ -113,14 +113,14 @@ def cpu_baseline(frames: np.ndarray, weights: np.ndarray, budget_s: float = 12.0
     """The oracle (CPU restatement of the reference's CPU paths) on a bounded sample, all host threads."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)   # passed explicitly: torchrun sets OMP_NUM_THREADS=1
     t0 = time.perf_counter()
-    O.fused(frames[0], KSIZE, weights=weights, threads=0)
+    O.fused(frames[0], KSIZE, weights=weights, threads=cores)
     t1 = time.perf_counter() - t0
     n = int(max(1, min(frames.shape[0], budget_s / max(t1, 1e-3))))
     t0 = time.perf_counter()
     for i in range(n):
-        O.fused(frames[i], KSIZE, weights=weights, threads=0)
+        O.fused(frames[i], KSIZE, weights=weights, threads=cores)
     dt = time.perf_counter() - t0
     return {"value": n * W * H / dt / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": "port",
             "sample": f"{n} of the {frames.shape[0]} 4K frames of one step, OpenMP over rows on {cores} threads "
@@ -134,16 +134,16 @@ def run_reference(args, rank: int) -> None:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     per_step = 2  # bounded sample: 2 of the 32 frames per step
     frames = synth_batch(per_step, 0xB200 + 4000)
     w = O.gauss_weights(KSIZE, SIGMA)
     for _ in range(args.warmup):
-        O.fused(frames[0], KSIZE, weights=w, threads=0)
+        O.fused(frames[0], KSIZE, weights=w, threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for i in range(per_step):
-            O.fused(frames[i], KSIZE, weights=w, threads=0)
+            O.fused(frames[i], KSIZE, weights=w, threads=cores)
     dt = time.perf_counter() - t0
     mpx = args.steps * per_step * W * H / dt / 1e6
     line = {"impl": "reference", "metric": "fused_4k_throughput", "value": mpx, "unit": "Mpixel/s", "n_gpus": args.gpus,
