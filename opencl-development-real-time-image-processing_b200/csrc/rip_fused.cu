@@ -121,7 +121,9 @@ static bool plan_weights_band(const float *w25, float g[3], double *band_out)
     const double u = std::ldexp(1.0, -24);
     double cum = 0.0;
     for (int i = 0; i < 25; i++) cum += (double)w25[i] * (25 - i);
-    const double band = 255.0 * dev + u * 255.0 * (cum + sum + 9.0 * sum) * 1.02 + 1e-6;
+    // (the bias rides in the horizontal FMA chain: its two inner results are rounded on the 2^-16 grid of
+    // [256, 512), i.e. by <= 256 u each, instead of relative to S~: + 512 u)
+    const double band = 255.0 * dev + u * (255.0 * (cum + sum + 9.0 * sum) + 512.0) * 1.02 + 1e-6;
     if (band > 0.05) return false;  // weights are not (close to) a symmetric separable kernel
     *band_out = band;
     return true;

@@ -305,7 +305,12 @@ __device__ __forceinline__ void blur_replay_warp(const u64 *F, uint32_t patch, u
 // row r - HALO.  The border rules are applied at run time (per-lane selects in x, two rare uniform
 // branches in y), so this is the only copy of the row body; the caller unrolls it by three with three
 // row buffers, which makes the buffer rotation and the two-row Sobel delay line register renames.
-template <int NPX, int CN, bool BGR, bool BLUR, bool SPECIAL>
+// What a copy of the row body has to check at run time:
+//   SPECIAL  head and tail rows of a segment: does this row store, do the next input row and the prefetched
+//            line exist, BORDER_REFLECT_101 in y.  The main loop's copies check none of that.
+//   EDGE     the warp's band holds image column 0 and/or W-1: per-lane border selects in x.  Interior warps
+//            (most) run copies without them.
+template <int NPX, int CN, bool BGR, bool BLUR, bool SPECIAL, bool EDGE>
 __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, const X2Params &xp, GeoX &geo, int r)
 {
     constexpr int NP = NPX / 2;
@@ -343,12 +348,16 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
             reload_pairs_if<NP, BLUR ? 8 : 16>(Q, pairs, flagged);
         }
 #endif
-        if ((unsigned)(r - geo.adv_lo) < (unsigned)geo.adv_n) geo.src += geo.in_pitch;
+        if constexpr (SPECIAL) {
+            if ((unsigned)(r - geo.adv_lo) < (unsigned)geo.adv_n) geo.src += geo.in_pitch;
+        } else {
+            geo.src += geo.in_pitch;   // (the main loop stops short of the rows where the band ends)
+        }
         load_row_x2<NPX, CN>(buf, geo.src);
 #if RIP_X2_L2PF > 0
         // pull the warp's bytes of a row further down into L2 (one 128-byte line per lane; pf_off is 0 in
         // the lanes that have no line to fetch and at the rows the band does not hold)
-        if (geo.pf_off != 0 && (unsigned)(r - geo.adv_lo) + RIP_X2_L2PF < (unsigned)geo.adv_n)
+        if (geo.pf_off != 0 && (!SPECIAL || (unsigned)(r - geo.adv_lo) + RIP_X2_L2PF < (unsigned)geo.adv_n))
             asm volatile("prefetch.global.L2 [%0];" ::"l"(geo.src + geo.pf_off));
 #endif
     }
@@ -374,10 +383,12 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
         // gray column, so the clamp applies to V: left of column 0 / right of column W-1 repeat it.
         float Vm2 = __shfl_up_sync(FULL, hi2(V[NP - 2]), 1), Vm1 = __shfl_up_sync(FULL, hi2(V[NP - 1]), 1);
         float Vp0 = __shfl_down_sync(FULL, lo2(V[0]), 1), Vp1 = __shfl_down_sync(FULL, lo2(V[1]), 1);
-        Vm2 = geo.e_left ? lo2(V[0]) : Vm2;
-        Vm1 = geo.e_left ? lo2(V[0]) : Vm1;
-        Vp0 = geo.e_right ? hi2(V[NP - 1]) : Vp0;
-        Vp1 = geo.e_right ? hi2(V[NP - 1]) : Vp1;
+        if constexpr (EDGE) {
+            Vm2 = geo.e_left ? lo2(V[0]) : Vm2;
+            Vm1 = geo.e_left ? lo2(V[0]) : Vm1;
+            Vp0 = geo.e_right ? hi2(V[NP - 1]) : Vp0;
+            Vp1 = geo.e_right ? hi2(V[NP - 1]) : Vp1;
+        }
         u64 P[NP + 4];
         P[0] = pk2(Vm2, lo2(V[NP - 2]));   // (V[-2], V[NP-2])
         P[1] = pk2(Vm1, lo2(V[NP - 1]));   // (V[-1], V[NP-1])
@@ -390,8 +401,8 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
 #pragma unroll
         for (int j = 0; j < NP; j++) {
             const u64 e2 = add2(P[j], P[j + 4]), e1 = add2(P[j + 1], P[j + 3]);
-            const u64 u = fma2(GH2, e2, fma2(GH1, e1, mul2(GH0, P[j + 2])));  // S~ of pixels j, j + NP
-            F[j] = add2(u, BIAS);                                            // floor(S~) in bits 15..22, fraction below
+            // S~ of pixels j, j + NP, plus the bias (it rides in the FMA chain): floor(S~) in bits 15..22, fraction below
+            F[j] = fma2(GH2, e2, fma2(GH1, e1, fma2(GH0, P[j + 2], BIAS)));
         }
         // guard band: the fraction bits within a ulps of 0 (mod 2^kFracBits)
         uint32_t zmin = 0xffffffffu;
@@ -445,10 +456,12 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
     // horizontal pass, BORDER_REFLECT_101 in x: gx = Vs[x+1] - Vs[x-1],  gy = Vd[x-1] + 2 Vd[x] + Vd[x+1]
     float sl = __shfl_up_sync(FULL, hi2(Vs[NP - 1]), 1), sr = __shfl_down_sync(FULL, lo2(Vs[0]), 1);
     float dl = __shfl_up_sync(FULL, hi2(Vd[NP - 1]), 1), dr = __shfl_down_sync(FULL, lo2(Vd[0]), 1);
-    sl = geo.e_left ? lo2(Vs[1]) : sl;             // x = -1 -> x = 1
-    dl = geo.e_left ? lo2(Vd[1]) : dl;
-    sr = geo.e_right ? hi2(Vs[NP - 2]) : sr;       // x = W  -> x = W-2
-    dr = geo.e_right ? hi2(Vd[NP - 2]) : dr;
+    if constexpr (EDGE) {
+        sl = geo.e_left ? lo2(Vs[1]) : sl;             // x = -1 -> x = 1
+        dl = geo.e_left ? lo2(Vd[1]) : dl;
+        sr = geo.e_right ? hi2(Vs[NP - 2]) : sr;       // x = W  -> x = W-2
+        dr = geo.e_right ? hi2(Vd[NP - 2]) : dr;
+    }
     // KS[k] = (e[k], e[k + NP]) with e[m] = Vs of pixel m - 1; KD likewise for Vd
     u64 KS[NP + 2], KD[NP + 2];
     KS[0] = pk2(sl, lo2(Vs[NP - 1]));
@@ -471,7 +484,7 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
             q[j] = lo2u(m);
             q[j + NP] = hi2u(m);
         }
-        const uint32_t ok = (r >= geo.r_store && r <= geo.r_last) ? geo.store_lane : 0u;
+        const uint32_t ok = (!SPECIAL || (r >= geo.r_store && r <= geo.r_last)) ? geo.store_lane : 0u;
         const uint32_t w0 = i2ip(q[1], q[0], i2ip(q[3], q[2], 0u));
         if constexpr (NPX == 8) {
             const uint32_t w1 = i2ip(q[5], q[4], i2ip(q[7], q[6], 0u));
@@ -488,6 +501,38 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
         st.F1[j] = F[j];
     }
     geo.dst += W;
+}
+
+// The rows of one segment.  Head: the warm-up rows and the first storing row (it may be frame row 0), one row
+// per trip with the SPECIAL copy of the row body and an explicit rotation of the three row buffers.  Main loop:
+// three rows per trip with the plain copy; the buffer rotation and the Sobel delay line are register renames
+// there.  Tail: the remaining rows (the last may be frame row H-1), SPECIAL again.  Only the main loop is hot,
+// so only its three copies of the row body need to stay in the instruction cache.
+template <int NPX, int CN, bool BGR, bool BLUR, bool EDGE>
+__device__ __forceinline__ void run_rows_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &b0, RawX<NPX, CN> &b1, RawX<NPX, CN> &b2,
+                                            const X2Params &xp, GeoX &geo, int r)
+{
+    const FusedParams &p = xp.f;
+#pragma unroll 1
+    for (; r <= geo.r_store && r < geo.r_last; r++) {
+        step_x2<NPX, CN, BGR, BLUR, true, EDGE>(st, b0, xp, geo, r);
+        const RawX<NPX, CN> t = b0; b0 = b1; b1 = b2; b2 = t;
+    }
+    // the main loop runs while all three rows of a trip store, and the row they load (three ahead) as well as
+    // the line they prefetch (RIP_X2_L2PF further) lie inside the band: step s advances freely iff
+    // s + 2 + RIP_X2_L2PF < in_row0 + in_rows - 1
+    const int r_main_last = min(geo.r_last - 1, p.in_row0 + p.in_rows - 4 - RIP_X2_L2PF);
+#pragma unroll 1
+    for (; r + 2 <= r_main_last; r += 3) {
+        step_x2<NPX, CN, BGR, BLUR, false, EDGE>(st, b0, xp, geo, r);
+        step_x2<NPX, CN, BGR, BLUR, false, EDGE>(st, b1, xp, geo, r + 1);
+        step_x2<NPX, CN, BGR, BLUR, false, EDGE>(st, b2, xp, geo, r + 2);
+    }
+#pragma unroll 1
+    for (; r <= geo.r_last; r++) {
+        step_x2<NPX, CN, BGR, BLUR, true, EDGE>(st, b0, xp, geo, r);
+        const RawX<NPX, CN> t = b0; b0 = b1; b1 = b2; b2 = t;
+    }
 }
 
 template <int NPX, int CN, bool BGR, bool BLUR>
@@ -571,25 +616,11 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     // output row produced by the step of input row r is r - HALO
     geo.dst = p.out + (size_t)frame * p.out_rows * W + (ptrdiff_t)(r - HALO - p.out_row0) * W + x;
 
-    // Head: the warm-up rows and the first storing row (it may be frame row 0), one row per trip with
-    // the SPECIAL copy of the row body and an explicit rotation of the three row buffers.  Main loop:
-    // three rows per trip with the plain copy; the buffer rotation and the Sobel delay line are register
-    // renames there.  Tail: the remaining one to three rows (the last may be frame row H-1), SPECIAL again.
-    // Only the main loop is hot, so only its three copies of the row body need to stay in the instruction cache.
-#pragma unroll 1
-    for (; r <= geo.r_store && r < geo.r_last; r++) {
-        step_x2<NPX, CN, BGR, BLUR, true>(st, b0, xp, geo, r);
-        const RawX<NPX, CN> t = b0; b0 = b1; b1 = b2; b2 = t;
-    }
-#pragma unroll 1
-    for (; r + 3 <= geo.r_last; r += 3) {
-        step_x2<NPX, CN, BGR, BLUR, false>(st, b0, xp, geo, r);
-        step_x2<NPX, CN, BGR, BLUR, false>(st, b1, xp, geo, r + 1);
-        step_x2<NPX, CN, BGR, BLUR, false>(st, b2, xp, geo, r + 2);
-    }
-#pragma unroll 1
-    for (; r <= geo.r_last; r++) {
-        step_x2<NPX, CN, BGR, BLUR, true>(st, b0, xp, geo, r);
-        const RawX<NPX, CN> t = b0; b0 = b1; b1 = b2; b2 = t;
-    }
+    // (the vote tells the compiler what it cannot see: the choice is the same in every lane)
+#ifdef RIP_X2_NOINTERIOR   // (experiment switch: one copy of the row loops for every warp)
+    run_rows_x2<NPX, CN, BGR, BLUR, true>(st, b0, b1, b2, xp, geo, r);
+#else
+    if (__any_sync(FULL, band == 0 || lane_last <= 31)) run_rows_x2<NPX, CN, BGR, BLUR, true>(st, b0, b1, b2, xp, geo, r);
+    else run_rows_x2<NPX, CN, BGR, BLUR, false>(st, b0, b1, b2, xp, geo, r);
+#endif
 }
