@@ -534,7 +534,7 @@ extern "C" int rip_gauss(int device, rip_stream stream, const uint8_t *d_in, uin
     Weights wts;
     if (int rc = load_weights(wts, ksize, weights, "rip_gauss")) return rc;
     DeviceGuard g(device);
-    return launch_blur_exact((cudaStream_t)stream, d_in, d_out, width, height, n_frames, channels, ksize, wts, 0, height, 0, height);
+    return launch_blur((cudaStream_t)stream, d_in, d_out, width, height, n_frames, channels, ksize, wts, 0, height, 0, height);
 }
 
 extern "C" int rip_sobel(int device, rip_stream stream, const uint8_t *d_in, uint8_t *d_out, int width, int height,
@@ -595,7 +595,7 @@ extern "C" int rip_fused(int device, rip_stream stream, const uint8_t *d_in, uin
     uint8_t *ws_gray = (uint8_t *)d_workspace;
     uint8_t *ws_blur = ws_gray + (size_t)width * in_rows * n_frames;
     if (int rc = launch_gray(s, d_in, ws_gray, (long long)width * in_rows * n_frames, in_format, RIP_GRAY_OUT_U8, device)) return rc;
-    if (int rc = launch_blur_exact(s, ws_gray, ws_blur, width, height, n_frames, 1, ksize, wts, in_row0, in_rows, b0, b1 - b0)) return rc;
+    if (int rc = launch_blur(s, ws_gray, ws_blur, width, height, n_frames, 1, ksize, wts, in_row0, in_rows, b0, b1 - b0)) return rc;
     return launch_sobel(s, ws_blur, d_out, width, height, n_frames, RIP_FMT_GRAY8, b0, b1 - b0, out_row0, out_rows);
 }
 
@@ -621,10 +621,14 @@ extern "C" int rip_debug_slow_path_stats(int device, int enable, uint64_t *slow_
     if (g_d_slow) RIP_CUDA(cudaMemset(g_d_slow, 0, sizeof(unsigned long long)));
     if (!enable && g_d_slow) {
         fused_set_slow_counter(nullptr);
+        blur_sep_set_slow_counter(nullptr);
         RIP_CUDA(cudaFree(g_d_slow));
         g_d_slow = nullptr;
     }
-    if (enable) fused_set_slow_counter(g_d_slow);
+    if (enable) {
+        fused_set_slow_counter(g_d_slow);
+        blur_sep_set_slow_counter(g_d_slow);
+    }
     return RIP_OK;
 }
 

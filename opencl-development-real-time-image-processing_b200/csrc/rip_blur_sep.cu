@@ -1,0 +1,255 @@
+// rip_blur_sep.cu -- the stand-alone KxK Gaussian (replaces kernel/gaussian_base.cl; results defined by the
+// reference's CPU path, GaussianBlur.cpp:231-261) at separable cost, bit-exact.
+//
+// The reference's value of a pixel/channel is trunc(clamp(S_ref, 0, 255)) with S_ref the sequential, unfused,
+// ky-major fp32 sum of the K*K rounded products.  Its weights (Controller.cpp:342-362 of src/GaussianBlur)
+// are a normalised Gaussian, i.e. separable up to float rounding.  This kernel evaluates a separable sum
+//   S~ = sum_ky g[ky] * ( sum_kx g[kx] * p[y+ky][x+kx] ),     g[k] = sqrt(w[k][k]),
+// (2K FMAs instead of K*K multiply-adds) and proves, per launch, a bound `band` on |S~ - S_ref|
+// (plan_sep_blur below).  S~ is formed on top of a bias of 256, which puts floor(S~) in mantissa bits 15..22
+// and the fraction in bits 0..14; a pixel whose fraction is farther than `band` from both 0 and 1 has
+// floor(S~) == floor(S_ref).  The others (~0.1 % per channel for 5x5, a few % for 17x17) replay the
+// reference's exact sequence from the same shared-memory tile.  Weights the bound cannot cover (not a
+// symmetric separable kernel) run the plain exact kernel in rip_stages.cu.
+//
+// Layout: a block of 256 threads produces a 32 x 32 tile.  The tile with its halo is loaded once with
+// clamp-to-edge coordinates (GaussianBlur.cpp:240-241), converted u8 -> fp32 once per loaded pixel (PRMT +
+// FADD: no I2F), and kept in shared memory as float4 (RGBA) or float (gray); the horizontal pass writes a
+// second shared array, the vertical pass reads it.  All shared-memory accesses of a warp are consecutive
+// 16-byte (or 4-byte) words: conflict-free.  HBM traffic: 8 algorithmic bytes per RGBA pixel; the halo
+// re-reads ((32+2h)^2 / 32^2) are L2 hits.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "rip_common.cuh"
+#include "rip_internal.h"
+
+namespace rip {
+
+namespace {
+
+constexpr int SEP_TW = 32, SEP_TH = 32, SEP_THREADS = 256;
+constexpr int kSepFracBits = 15;
+constexpr float kSepBias = 256.0f;
+
+struct SepParams {
+    const uint8_t *src;
+    uint8_t *dst;
+    int W, H, src_row0, src_rows, out_row0, out_rows, ksize;
+    uint32_t zoff, zthr;        // replay iff ((bits << 17) + zoff) < zthr
+    float g[RIP_MAX_KSIZE];     // separable taps
+    unsigned long long *slow_counter;   // optional statistics (NULL in production)
+};
+
+template <int CN> struct SepPx;
+template <> struct SepPx<4> {
+    typedef float4 T;
+    typedef uint32_t raw_t;
+    static __device__ __forceinline__ T load(const uint8_t *p)
+    {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(p));
+        // 0x4B000000 | byte is the float 8388608 + byte
+        const float m = 8388608.0f;
+        return make_float4(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440)) - m, __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7441)) - m,
+                           __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7442)) - m, __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7443)) - m);
+    }
+    static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ T splat(float b) { return make_float4(b, b, b, b); }
+    static __device__ __forceinline__ T fma(float g, T v, T a) { return make_float4(fmaf(g, v.x, a.x), fmaf(g, v.y, a.y), fmaf(g, v.z, a.z), fmaf(g, v.w, a.w)); }
+    static __device__ __forceinline__ T mul(float g, T v) { return make_float4(g * v.x, g * v.y, g * v.z, g * v.w); }
+    // the reference's step: acc = fl(acc + fl(v * w)), no FMA
+    static __device__ __forceinline__ T ref_step(T a, T v, float w)
+    {
+        return make_float4(__fadd_rn(a.x, __fmul_rn(v.x, w)), __fadd_rn(a.y, __fmul_rn(v.y, w)), __fadd_rn(a.z, __fmul_rn(v.z, w)),
+                           __fadd_rn(a.w, __fmul_rn(v.w, w)));
+    }
+    static __device__ __forceinline__ uint32_t zmin(T f, uint32_t zoff)
+    {
+        const uint32_t a = (__float_as_uint(f.x) << (32 - kSepFracBits)) + zoff, b = (__float_as_uint(f.y) << (32 - kSepFracBits)) + zoff;
+        const uint32_t c = (__float_as_uint(f.z) << (32 - kSepFracBits)) + zoff, d = (__float_as_uint(f.w) << (32 - kSepFracBits)) + zoff;
+        return min(__vimin3_u32(a, b, c), d);
+    }
+    static __device__ __forceinline__ uint32_t pack_fast(T f)   // floor(S~) of each channel: mantissa bits 15..22
+    {
+        return ((__float_as_uint(f.x) >> kSepFracBits) & 0xffu) | (((__float_as_uint(f.y) >> kSepFracBits) & 0xffu) << 8) |
+               (((__float_as_uint(f.z) >> kSepFracBits) & 0xffu) << 16) | (((__float_as_uint(f.w) >> kSepFracBits) & 0xffu) << 24);
+    }
+    static __device__ __forceinline__ uint32_t pack_exact(T a)  // (uchar)clamp(sum, 0, 255), GaussianBlur.cpp:255-258
+    {
+        return (uint32_t)__float2int_rz(fminf(fmaxf(a.x, 0.f), 255.f)) | ((uint32_t)__float2int_rz(fminf(fmaxf(a.y, 0.f), 255.f)) << 8) |
+               ((uint32_t)__float2int_rz(fminf(fmaxf(a.z, 0.f), 255.f)) << 16) | ((uint32_t)__float2int_rz(fminf(fmaxf(a.w, 0.f), 255.f)) << 24);
+    }
+    static __device__ __forceinline__ void store(uint8_t *p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
+};
+template <> struct SepPx<1> {
+    typedef float T;
+    typedef uint8_t raw_t;
+    static __device__ __forceinline__ T load(const uint8_t *p) { return __uint_as_float(0x4B000000u | (uint32_t)__ldg(p)) - 8388608.0f; }
+    static __device__ __forceinline__ T zero() { return 0.f; }
+    static __device__ __forceinline__ T splat(float b) { return b; }
+    static __device__ __forceinline__ T fma(float g, T v, T a) { return fmaf(g, v, a); }
+    static __device__ __forceinline__ T mul(float g, T v) { return g * v; }
+    static __device__ __forceinline__ T ref_step(T a, T v, float w) { return __fadd_rn(a, __fmul_rn(v, w)); }
+    static __device__ __forceinline__ uint32_t zmin(T f, uint32_t zoff) { return (__float_as_uint(f) << (32 - kSepFracBits)) + zoff; }
+    static __device__ __forceinline__ uint32_t pack_fast(T f) { return (__float_as_uint(f) >> kSepFracBits) & 0xffu; }
+    static __device__ __forceinline__ uint32_t pack_exact(T a) { return (uint32_t)__float2int_rz(fminf(fmaxf(a, 0.f), 255.f)); }
+    static __device__ __forceinline__ void store(uint8_t *p, uint32_t v) { *p = (uint8_t)v; }
+};
+
+// KT = compile-time kernel size (unrolled tap loops), or 0 = the run-time size in p.ksize
+template <int CN, int KT>
+__global__ void __launch_bounds__(SEP_THREADS)
+blur_sep_kernel(const __grid_constant__ SepParams p, const __grid_constant__ Weights wts)
+{
+    typedef SepPx<CN> P;
+    typedef typename P::T T;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int K = KT ? KT : p.ksize;
+    const int half = K >> 1;
+    const int tws = SEP_TW + 2 * half, th = SEP_TH + 2 * half;
+    T *tile = reinterpret_cast<T *>(smem_raw);   // [th][tws]  the input tile with halo, as fp32
+    T *hbuf = tile + th * tws;                   // [th][SEP_TW] after the horizontal pass
+
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * SEP_TW, y0 = p.out_row0 + blockIdx.y * SEP_TH;
+    const uint8_t *fsrc = p.src + (size_t)blockIdx.z * p.src_rows * p.W * CN;
+    uint8_t *fdst = p.dst + (size_t)blockIdx.z * p.out_rows * p.W * CN;
+
+    // ---- 1. tile with halo, clamp-to-edge; rows below the last row this band's outputs need are never
+    //         consumed and may lie outside src: zero
+    const int y_last = min(p.out_row0 + p.out_rows, p.H) - 1 + half;
+    for (int ty = wrp; ty < th; ty += SEP_THREADS / 32) {
+        const int gy_raw = y0 - half + ty;
+        const bool row_ok = gy_raw <= y_last;
+        const uint8_t *row = fsrc + (size_t)(clampi(gy_raw, 0, p.H - 1) - p.src_row0) * p.W * CN;
+        for (int tx = lane; tx < tws; tx += 32)
+            tile[ty * tws + tx] = row_ok ? P::load(row + (size_t)clampi(x0 - half + tx, 0, p.W - 1) * CN) : P::zero();
+    }
+    __syncthreads();
+
+    // ---- 2. horizontal pass: hbuf[ty][x] = sum_k g[k] * tile[ty][x + k]   (one FMA chain, k ascending)
+    for (int ty = wrp; ty < th; ty += SEP_THREADS / 32) {
+        const T *t = tile + ty * tws + lane;
+        T acc = P::mul(p.g[0], t[0]);
+#pragma unroll
+        for (int k = 1; k < (KT ? KT : 1); k++) acc = P::fma(p.g[k], t[k], acc);
+        if (!KT)
+            for (int k = 1; k < K; k++) acc = P::fma(p.g[k], t[k], acc);
+        hbuf[ty * SEP_TW + lane] = acc;
+    }
+    __syncthreads();
+
+    // ---- 3. vertical pass on top of the bias, guard band, exact replay of the pixels inside it
+    const int x = x0 + lane;
+#pragma unroll 1
+    for (int oy = wrp; oy < SEP_TH; oy += SEP_THREADS / 32) {
+        const int y = y0 + oy;
+        if (y >= p.out_row0 + p.out_rows || y >= p.H) break;   // warp-uniform
+        const T *h = hbuf + oy * SEP_TW + lane;
+        T f = P::fma(p.g[0], h[0], P::splat(kSepBias));
+#pragma unroll
+        for (int k = 1; k < (KT ? KT : 1); k++) f = P::fma(p.g[k], h[k * SEP_TW], f);
+        if (!KT)
+            for (int k = 1; k < K; k++) f = P::fma(p.g[k], h[k * SEP_TW], f);
+        uint32_t out = P::pack_fast(f);
+        if (P::zmin(f, p.zoff) < p.zthr) {
+            // the reference's sequence (GaussianBlur.cpp:236-258): ky-major / kx-minor from 0.0f, unfused
+            const T *t = tile + oy * tws + lane;
+            T acc = P::zero();
+            for (int ky = 0; ky < K; ky++)
+                for (int kx = 0; kx < K; kx++) acc = P::ref_step(acc, t[ky * tws + kx], wts.w[ky * K + kx]);
+            out = P::pack_exact(acc);
+            if (p.slow_counter) atomicAdd(p.slow_counter, 1ull);
+        }
+        if (x < p.W) P::store(fdst + ((size_t)(y - p.out_row0) * p.W + x) * CN, out);
+    }
+}
+
+unsigned long long *g_sep_slow_counter = nullptr;
+
+}  // namespace
+
+void blur_sep_set_slow_counter(unsigned long long *d_counter) { g_sep_slow_counter = d_counter; }
+
+// Separable taps and the guard band for them.  With u = 2^-24, all weights >= 0, sum = sum(w), pixel values <= 255:
+//   reference:  acc_k = fl(acc_{k-1} + fl(p_k w_k)); each add errs by <= u |acc_k| <= u 255 (w_0 + .. + w_k), each
+//               product by <= u 255 w_k:   |S_ref - S| <= u 255 (sum_i w_i (K*K - i) + sum)
+//   separable model:  |S - S_sep| <= 255 sum_ij |w_ij - g_i g_j|            (S_sep = the exact separable sum)
+//   horizontal FMA chain: result k is <= 255 G_k (G_k = g_0 + .. + g_k) and rounded once: error <= u 255 sum_k G_k,
+//               which the vertical taps scale by sum(g)
+//   vertical FMA chain on top of the bias: every result lies in [256, 512) and is rounded on that binade's 2^-16
+//               half-ulp: <= K 2^-16 (the last of them is the +1/2 in `a` below; counted here as well)
+//   margin 2 % + 1e-6 on top.
+static bool plan_sep_blur(const float *w, int K, float *g, double *band_out)
+{
+    double sum = 0.0, cum = 0.0;
+    for (int i = 0; i < K * K; i++) {
+        if (!(w[i] >= 0.0f) || !std::isfinite(w[i])) return false;
+        sum += (double)w[i];
+        cum += (double)w[i] * (K * K - i);
+    }
+    if (!(sum > 0.0) || 255.0 * sum >= 255.9) return false;   // floor(S) must stay <= 255
+    for (int k = 0; k < K; k++) g[k] = (float)std::sqrt((double)w[k * K + k]);
+    double dev = 0.0, gsum = 0.0, gpart = 0.0, gcum = 0.0;
+    for (int i = 0; i < K; i++)
+        for (int j = 0; j < K; j++) dev += std::fabs((double)w[i * K + j] - (double)g[i] * (double)g[j]);
+    for (int k = 0; k < K; k++) {
+        gsum += (double)g[k];
+        gpart += (double)g[k];
+        gcum += gpart;
+    }
+    const double u = std::ldexp(1.0, -24);
+    const double band = (255.0 * dev + u * 255.0 * (cum + sum) + u * 255.0 * gcum * gsum + K * std::ldexp(1.0, -16)) * 1.02 + 1e-6;
+    if (band > 0.05) return false;   // not (close to) a symmetric separable kernel: the exact kernel handles it
+    *band_out = band;
+    return true;
+}
+
+template <int CN>
+static int launch_sep_cn(cudaStream_t s, const SepParams &p, const Weights &wts, dim3 grid, size_t smem)
+{
+    void (*kern)(SepParams, Weights);
+    switch (p.ksize) {
+    case 3:  kern = blur_sep_kernel<CN, 3>; break;
+    case 5:  kern = blur_sep_kernel<CN, 5>; break;
+    case 7:  kern = blur_sep_kernel<CN, 7>; break;
+    case 9:  kern = blur_sep_kernel<CN, 9>; break;
+    case 17: kern = blur_sep_kernel<CN, 17>; break;
+    default: kern = blur_sep_kernel<CN, 0>; break;
+    }
+    if (smem > 48 * 1024) RIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, SEP_THREADS, smem, s>>>(p, wts);
+    RIP_LAUNCH_CHECK();
+    return RIP_OK;
+}
+
+// returns RIP_EUNSUPPORTED (without recording an error) when the weights or the shape need the exact kernel
+int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int H, int n_frames, int cn, int ksize,
+                    const Weights &wts, int src_row0, int src_rows, int out_row0, int out_rows)
+{
+    if ((cn != 1 && cn != 4) || ksize < 3) return RIP_EUNSUPPORTED;
+    if (getenv("RIP_BLUR_EXACT")) return RIP_EUNSUPPORTED;   // (tests compare the two kernels)
+    if (cn == 4 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u)) return RIP_EUNSUPPORTED;
+    SepParams p;
+    memset(&p, 0, sizeof(p));
+    double band = 0.0;
+    if (!plan_sep_blur(wts.w, ksize, p.g, &band)) return RIP_EUNSUPPORTED;
+    p.src = src; p.dst = dst; p.W = W; p.H = H;
+    p.src_row0 = src_row0; p.src_rows = src_rows; p.out_row0 = out_row0; p.out_rows = out_rows; p.ksize = ksize;
+    p.slow_counter = g_sep_slow_counter;
+    // F = S~ + 256 is rounded to a multiple of ulp = 2^-15 (error <= ulp/2): a pixel whose 15 fraction bits are
+    // >= a and <= 2^15 - 1 - a has S~ at least `band` away from every integer when a >= band / ulp + 1/2
+    const double ulp = std::ldexp(1.0, -kSepFracBits);
+    const uint32_t a = (uint32_t)std::ceil(band / ulp + 0.5);
+    p.zoff = a << (32 - kSepFracBits);
+    p.zthr = (2u * a) << (32 - kSepFracBits);
+    const int half = ksize >> 1;
+    const size_t elem = cn == 4 ? sizeof(float4) : sizeof(float);
+    const size_t smem = ((size_t)(SEP_TH + 2 * half) * (SEP_TW + 2 * half) + (size_t)(SEP_TH + 2 * half) * SEP_TW) * elem;
+    const dim3 grid((W + SEP_TW - 1) / SEP_TW, (out_rows + SEP_TH - 1) / SEP_TH, n_frames);
+    if (grid.y > 65535u || grid.z > 65535u) return RIP_EUNSUPPORTED;
+    return cn == 4 ? launch_sep_cn<4>(s, p, wts, grid, smem) : launch_sep_cn<1>(s, p, wts, grid, smem);
+}
+
+}  // namespace rip

@@ -616,11 +616,15 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     // output row produced by the step of input row r is r - HALO
     geo.dst = p.out + (size_t)frame * p.out_rows * W + (ptrdiff_t)(r - HALO - p.out_row0) * W + x;
 
-    // (the vote tells the compiler what it cannot see: the choice is the same in every lane)
-#ifdef RIP_X2_NOINTERIOR   // (experiment switch: one copy of the row loops for every warp)
-    run_rows_x2<NPX, CN, BGR, BLUR, true>(st, b0, b1, b2, xp, geo, r);
-#else
+    // One copy of the row loops for every warp.  A second copy without the border selects for the warps whose
+    // band touches neither image edge (-4 % instructions on their hot path) was measured at 525 us instead of
+    // 418 us per 32 4K frames: with both copies live on an SM the main loops no longer fit the instruction
+    // cache (no_instruction stalls 0.17 -> 1.86 warps per issue).  RIP_X2_INTERIOR re-enables it for experiments
+    // (the vote tells the compiler what it cannot see: the choice is the same in every lane).
+#ifdef RIP_X2_INTERIOR
     if (__any_sync(FULL, band == 0 || lane_last <= 31)) run_rows_x2<NPX, CN, BGR, BLUR, true>(st, b0, b1, b2, xp, geo, r);
     else run_rows_x2<NPX, CN, BGR, BLUR, false>(st, b0, b1, b2, xp, geo, r);
+#else
+    run_rows_x2<NPX, CN, BGR, BLUR, true>(st, b0, b1, b2, xp, geo, r);
 #endif
 }

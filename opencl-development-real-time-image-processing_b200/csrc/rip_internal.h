@@ -10,8 +10,16 @@ namespace rip {
 
 // rip_stages.cu
 int launch_gray(cudaStream_t s, const uint8_t *in, uint8_t *out, long long npx, int fmt, int out_mode, int device);
+// KxK Gaussian: the separable guard-band kernel (rip_blur_sep.cu) when the weights allow it, else the plain
+// reference-order kernel (rip_stages.cu); both bit-exact
+int launch_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int H, int n_frames, int cn,
+                int ksize, const Weights &wts, int src_row0, int src_rows, int out_row0, int out_rows);
 int launch_blur_exact(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int H, int n_frames, int cn,
                       int ksize, const Weights &wts, int src_row0, int src_rows, int out_row0, int out_rows);
+// rip_blur_sep.cu; RIP_EUNSUPPORTED (no error recorded) = use the exact kernel
+int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int H, int n_frames, int cn,
+                    int ksize, const Weights &wts, int src_row0, int src_rows, int out_row0, int out_rows);
+void blur_sep_set_slow_counter(unsigned long long *d_counter);
 int launch_sobel(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int H, int n_frames, int fmt,
                  int src_row0, int src_rows, int out_row0, int out_rows);
 

@@ -199,6 +199,14 @@ int launch_blur_exact(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, i
     return RIP_OK;
 }
 
+int launch_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int H, int n_frames, int cn,
+                int ksize, const Weights &wts, int src_row0, int src_rows, int out_row0, int out_rows)
+{
+    const int rc = launch_blur_sep(s, src, dst, W, H, n_frames, cn, ksize, wts, src_row0, src_rows, out_row0, out_rows);
+    if (rc != RIP_EUNSUPPORTED) return rc;
+    return launch_blur_exact(s, src, dst, W, H, n_frames, cn, ksize, wts, src_row0, src_rows, out_row0, out_rows);
+}
+
 // ---------------------------------------------------------------------------------------------
 // 3x3 Sobel magnitude (OpenCV semantics).  A 64x16 output tile per block; the gray tile with its
 // 1-pixel BORDER_REFLECT_101 halo is built in shared memory (converted from colour on the fly when

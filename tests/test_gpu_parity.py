@@ -113,6 +113,56 @@ def test_blur_flat_regions_sigma15_lose_one_level(ctx, oracle):
     assert (got == 255).all()
 
 
+def _adversarial_rgba(h, w):
+    """constants, ramps, 1-px checkerboard, bright corner pixels."""
+    yy, xx = np.mgrid[0:h, 0:w]
+    frames = [np.full((h, w), v, np.uint8) for v in (0, 255, 1, 2, 4, 254, 77)]
+    frames += [(xx * 255 // max(w - 1, 1)).astype(np.uint8), (yy * 255 // max(h - 1, 1)).astype(np.uint8),
+               (((xx + yy) & 1) * 255).astype(np.uint8)]
+    corners = np.zeros((h, w), np.uint8)
+    corners[0, 0] = corners[0, -1] = corners[-1, 0] = corners[-1, -1] = corners[h // 2, 0] = corners[0, w // 2] = 255
+    frames.append(corners)
+    return [np.ascontiguousarray(np.stack([f, f[::-1], f[:, ::-1], 255 - f], -1)) for f in frames]
+
+
+@pytest.mark.parametrize("k,sigma", [(5, 1.0), (5, 1.5), (9, 2.5), (17, 6.0)])
+def test_blur_separable_kernel_equals_exact_kernel_and_oracle(ctx, oracle, k, sigma, monkeypatch):
+    """The separable guard-band kernel (default) and the reference-order kernel (RIP_BLUR_EXACT) must agree bit for bit."""
+    w = rip.gauss_weights(k, sigma)
+    imgs = [synth_frame("uniform", 70, 101, 3, 4), synth_frame("smooth", 33, 64, 4, 4)] + _adversarial_rgba(37, 45)
+    for i, img in enumerate(imgs):
+        want = oracle.blur(img, k, weights=w, threads=0)
+        monkeypatch.delenv("RIP_BLUR_EXACT", raising=False)
+        _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), want, f"separable blur K={k} frame {i}")
+        g = np.ascontiguousarray(img[..., 0])
+        _eq(ctx.process(g, rip.OP_GAUSSIAN, rip.FMT_GRAY8, ksize=k, weights=w), oracle.blur(g, k, weights=w, threads=0),
+            f"separable blur gray K={k} frame {i}")
+        monkeypatch.setenv("RIP_BLUR_EXACT", "1")
+        _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), want, f"exact blur K={k} frame {i}")
+
+
+def test_blur_guard_band_statistics_and_non_separable_weights(ctx, oracle):
+    """The replay must trigger (flat frames: always) yet stay rare on noise; weights that are not a symmetric
+    separable kernel must take the reference-order kernel and still match."""
+    h, wd = 96, 160
+    d_out = rip.DeviceBuffer(h * wd * 4)
+    w = rip.gauss_weights(5, 1.0)
+    for kind, lo, hi in (("uniform", 1e-5, 2e-2), ("flat", 0.9, 1.1)):
+        img = synth_frame("uniform", h, wd, 72, 4) if kind == "uniform" else np.full((h, wd, 4), 77, np.uint8)
+        d_in = rip.DeviceBuffer(img.nbytes).upload(img)
+        rip.slow_path_stats(True)
+        rip.gauss_dev(d_in.ptr, d_out.ptr, wd, h, 1, 4, 5, w)
+        frac = rip.slow_path_stats(False) / (h * wd)
+        assert lo <= frac <= hi, (kind, frac)
+    rng = np.random.default_rng(5)
+    wr = rng.random((5, 5)).astype(np.float32)
+    wr /= wr.sum() * np.float32(1.001)
+    img = synth_frame("uniform", 40, 52, 9, 4)
+    rip.slow_path_stats(True)
+    _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=5, weights=wr), oracle.blur(img, 5, weights=wr, threads=0), "random weights")
+    assert rip.slow_path_stats(False) == 0   # the separable kernel did not run
+
+
 def test_blur_rejects_bad_arguments(ctx):
     img = np.zeros((8, 8, 4), np.uint8)
     with pytest.raises(rip.RipError):
