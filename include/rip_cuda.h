@@ -47,7 +47,11 @@ typedef struct rip_kernel rip_kernel;  /* kernel variant handle; replaces cl_ker
 typedef struct rip_event rip_event;    /* cudaEvent_t wrapper;  replaces cl_event */
 
 /* pixel formats of the interleaved u8 images */
-enum { RIP_FMT_GRAY8 = 1, RIP_FMT_RGB8 = 3, RIP_FMT_RGBA8 = 4, RIP_FMT_BGR8 = 5, RIP_FMT_BGRA8 = 6 };
+enum { RIP_FMT_GRAY8 = 1, RIP_FMT_RGB8 = 3, RIP_FMT_RGBA8 = 4, RIP_FMT_BGR8 = 5, RIP_FMT_BGRA8 = 6, RIP_FMT_NV12 = 7 };
+/* RIP_FMT_NV12 (the reference's camera format, RT/RealtimeImageProcessing.cpp:153): per frame a W*H luma plane
+ * followed by the W*H/2 interleaved chroma plane (frame = W*H*3/2 bytes, H even).  Accepted by the EDGE and FUSED
+ * operations only; the luma plane is the gray image (one byte per pixel leaves HBM instead of three or four),
+ * the chroma plane is never read.  Row bands of an NV12 frame are passed as plain luma rows. */
 
 /* operations (the reference's METHOD strings "GRAYSCALE" / "GAUSSIAN" / "EDGE", plus "FUSED") */
 enum { RIP_OP_GRAY = 0, RIP_OP_EDGE = 1, RIP_OP_GAUSSIAN = 2, RIP_OP_FUSED = 3 };

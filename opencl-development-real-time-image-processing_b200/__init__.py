@@ -20,11 +20,11 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RIP_LIB_PATH") or os.path.join(_PKG, "librip_cuda.so")
 
 # ---- constants (include/rip_cuda.h) ----
-FMT_GRAY8, FMT_RGB8, FMT_RGBA8, FMT_BGR8, FMT_BGRA8 = 1, 3, 4, 5, 6
+FMT_GRAY8, FMT_RGB8, FMT_RGBA8, FMT_BGR8, FMT_BGRA8, FMT_NV12 = 1, 3, 4, 5, 6, 7
 OP_GRAY, OP_EDGE, OP_GAUSSIAN, OP_FUSED = 0, 1, 2, 3
 GRAY_OUT_U8, GRAY_OUT_RGBA = 0, 1
 MAX_KSIZE = 31
-CHANNELS = {FMT_GRAY8: 1, FMT_RGB8: 3, FMT_BGR8: 3, FMT_RGBA8: 4, FMT_BGRA8: 4}
+CHANNELS = {FMT_GRAY8: 1, FMT_RGB8: 3, FMT_BGR8: 3, FMT_RGBA8: 4, FMT_BGRA8: 4, FMT_NV12: 1}
 
 # every symbol include/rip_cuda.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -338,7 +338,8 @@ class Context:
 
     def process(self, frames: np.ndarray, op: int, fmt: int, *, gray_out=GRAY_OUT_U8, ksize=0, weights=None,
                 out: np.ndarray | None = None, banded: bool = False, prof: bool = False):
-        """frames: (N, H, W, C) or (H, W, C) / (H, W) u8 host array (pageable or pinned)."""
+        """frames: (N, H, W, C) or (H, W, C) / (H, W) u8 host array (pageable or pinned); NV12: (N, H*3/2, W) or
+        (H*3/2, W), the luma plane followed by the chroma plane."""
         a = frames
         assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"]
         cn = CHANNELS[fmt]
@@ -346,6 +347,9 @@ class Context:
             if a.ndim == 2:
                 a = a[None]
             n, h, w = a.shape
+            if fmt == FMT_NV12:
+                assert h % 3 == 0
+                h = h * 2 // 3
         else:
             if a.ndim == 3:
                 a = a[None]

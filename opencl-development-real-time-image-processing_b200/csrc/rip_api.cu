@@ -73,11 +73,18 @@ static int check_device(int device)
 static int channels_of(int fmt)
 {
     switch (fmt) {
-    case RIP_FMT_GRAY8: return 1;
+    case RIP_FMT_GRAY8: case RIP_FMT_NV12: return 1;   // (NV12: the luma plane is the image)
     case RIP_FMT_RGB8: case RIP_FMT_BGR8: return 3;
     case RIP_FMT_RGBA8: case RIP_FMT_BGRA8: return 4;
     default: return 0;
     }
+}
+
+// bytes from one frame of a batch to the next
+static size_t frame_bytes_of(int fmt, int width, int height)
+{
+    if (fmt == RIP_FMT_NV12) return (size_t)width * height * 3 / 2;
+    return (size_t)width * height * channels_of(fmt);
 }
 
 static int load_weights(Weights &dst, int ksize, const float *weights, const char *who)
@@ -544,10 +551,13 @@ extern "C" int rip_sobel(int device, rip_stream stream, const uint8_t *d_in, uin
     if (int rc = check_image("rip_sobel", d_in, d_out, width, height, n_frames)) return rc;
     if (channels_of(in_format) == 0) return fail(RIP_EINVAL, "rip_sobel: unsupported input format %d", in_format);
     DeviceGuard g(device);
-    if (in_format != RIP_FMT_GRAY8 && fused_supported(width, height, in_format, 0, d_in, d_out))
+    if (fused_supported(width, height, in_format, 0, d_in, d_out))
         return launch_fused((cudaStream_t)stream, d_in, d_out, width, height, n_frames, in_format, false, nullptr, 0, height, 0,
                             height, device);
-    return launch_sobel((cudaStream_t)stream, d_in, d_out, width, height, n_frames, in_format, 0, height, 0, height);
+    if (in_format == RIP_FMT_NV12 && n_frames > 1)
+        return fail(RIP_EUNSUPPORTED, "rip_sobel: NV12 batches need width %% 4 == 0, an even height and 4-byte aligned buffers");
+    return launch_sobel((cudaStream_t)stream, d_in, d_out, width, height, n_frames, in_format == RIP_FMT_NV12 ? RIP_FMT_GRAY8 : in_format, 0,
+                        height, 0, height);
 }
 
 extern "C" int rip_fused_workspace_bytes(int width, int in_rows, int n_frames, int ksize, size_t *bytes)
@@ -567,7 +577,7 @@ extern "C" int rip_fused(int device, rip_stream stream, const uint8_t *d_in, uin
     if (int rc = check_device(device)) return rc;
     if (int rc = check_image("rip_fused", d_in, d_out, width, height, n_frames)) return rc;
     const int cn = channels_of(in_format);
-    if (cn < 3) return fail(RIP_EINVAL, "rip_fused: input must be a colour format (got %d)", in_format);
+    if (cn == 0) return fail(RIP_EINVAL, "rip_fused: unsupported input format %d", in_format);
     Weights wts;
     if (int rc = load_weights(wts, ksize, weights, "rip_fused")) return rc;
     const int half = ksize / 2;
@@ -594,7 +604,13 @@ extern "C" int rip_fused(int device, rip_stream stream, const uint8_t *d_in, uin
         return fail(RIP_EINVAL, "rip_fused: this shape runs the staged path and needs %zu bytes of workspace (got %zu)", need, workspace_bytes);
     uint8_t *ws_gray = (uint8_t *)d_workspace;
     uint8_t *ws_blur = ws_gray + (size_t)width * in_rows * n_frames;
-    if (int rc = launch_gray(s, d_in, ws_gray, (long long)width * in_rows * n_frames, in_format, RIP_GRAY_OUT_U8, device)) return rc;
+    if (cn == 1) {   // the input is the gray image already
+        if (in_format == RIP_FMT_NV12 && n_frames > 1)
+            return fail(RIP_EUNSUPPORTED, "rip_fused: NV12 batches run the single-kernel path only (5x5 weights, width %% 4 == 0, aligned buffers)");
+        ws_gray = const_cast<uint8_t *>(d_in);
+    } else if (int rc = launch_gray(s, d_in, ws_gray, (long long)width * in_rows * n_frames, in_format, RIP_GRAY_OUT_U8, device)) {
+        return rc;
+    }
     if (int rc = launch_blur(s, ws_gray, ws_blur, width, height, n_frames, 1, ksize, wts, in_row0, in_rows, b0, b1 - b0)) return rc;
     return launch_sobel(s, ws_blur, d_out, width, height, n_frames, RIP_FMT_GRAY8, b0, b1 - b0, out_row0, out_rows);
 }
@@ -709,11 +725,10 @@ int validate_desc(const rip_op_desc *desc, int *cn_out)
     case RIP_OP_EDGE:
         break;
     case RIP_OP_GAUSSIAN:
-        if (cn != 1 && cn != 4) return fail(RIP_EINVAL, "GAUSSIAN runs on GRAY8 or RGBA8/BGRA8 input");
+        if ((cn != 1 && cn != 4) || desc->in_format == RIP_FMT_NV12) return fail(RIP_EINVAL, "GAUSSIAN runs on GRAY8 or RGBA8/BGRA8 input");
         if (!desc->weights) return fail(RIP_EINVAL, "GAUSSIAN needs weights");
         break;
     case RIP_OP_FUSED:
-        if (cn < 3) return fail(RIP_EINVAL, "FUSED needs a colour input");
         if (!desc->weights) return fail(RIP_EINVAL, "FUSED needs weights");
         break;
     default:
@@ -831,7 +846,8 @@ extern "C" int rip_process_host(rip_ctx *ctx, const rip_op_desc *desc, const uin
     job.W = width;
     job.H = height;
     if (int rc = validate_desc(desc, &job.cn)) return rc;
-    job.in_frame_bytes = (size_t)width * height * job.cn;
+    if (desc->in_format == RIP_FMT_NV12 && (height & 1)) return fail(RIP_EINVAL, "NV12 frames need an even height (got %d)", height);
+    job.in_frame_bytes = frame_bytes_of(desc->in_format, width, height);
     if (int rc = rip_out_bytes_per_frame(desc, width, height, &job.out_frame_bytes)) return rc;
 
     const int nd = (int)ctx->devs.size();
@@ -906,11 +922,12 @@ extern "C" int rip_process_host_banded(rip_ctx *ctx, const rip_op_desc *desc, co
                     if (desc->op == RIP_OP_FUSED) {
                         rc = rip_fused(dev.device, b.stream, (const uint8_t *)b.d_in, (uint8_t *)b.d_out, width, height, 1,
                                        desc->in_format, desc->ksize, desc->weights, i0, i1 - i0, o0, o1 - o0, b.d_ws, b.ws_cap);
-                    } else if (desc->in_format != RIP_FMT_GRAY8 && fused_supported(width, height, desc->in_format, 0, (const uint8_t *)b.d_in, (uint8_t *)b.d_out)) {
+                    } else if (fused_supported(width, height, desc->in_format, 0, (const uint8_t *)b.d_in, (uint8_t *)b.d_out)) {
                         rc = launch_fused(b.stream, (const uint8_t *)b.d_in, (uint8_t *)b.d_out, width, height, 1, desc->in_format, false,
                                           nullptr, i0, i1 - i0, o0, o1 - o0, dev.device);
                     } else {
-                        rc = launch_sobel(b.stream, (const uint8_t *)b.d_in, (uint8_t *)b.d_out, width, height, 1, desc->in_format, i0,
+                        rc = launch_sobel(b.stream, (const uint8_t *)b.d_in, (uint8_t *)b.d_out, width, height, 1,
+                                          desc->in_format == RIP_FMT_NV12 ? RIP_FMT_GRAY8 : desc->in_format, i0,
                                           i1 - i0, o0, o1 - o0);
                     }
                     if (rc) break;

@@ -53,6 +53,7 @@ struct FusedParams {
     uint8_t *out;
     int W, H;
     int in_row0, in_rows, out_row0, out_rows;
+    size_t in_frame_bytes;   // distance between the frames of the input batch (NV12: the luma plane plus the chroma plane)
     int seg_rows, n_segs, n_bands, n_band_groups;
     float w[25];         // exact 2-D weights for the replay
     unsigned long long *slow_counter;  // optional statistics (NULL in production)
@@ -84,8 +85,10 @@ bool fused_supported(int W, int H, int fmt, int ksize, const uint8_t *d_in, cons
 {
     if (ksize != 0 && ksize != 5) return false;
     if (W < 4 || (W & 3) || H < 2) return false;
-    const int cn = (fmt == RIP_FMT_RGB8 || fmt == RIP_FMT_BGR8) ? 3 : (fmt == RIP_FMT_RGBA8 || fmt == RIP_FMT_BGRA8) ? 4 : 0;
+    const int cn = (fmt == RIP_FMT_RGB8 || fmt == RIP_FMT_BGR8) ? 3 : (fmt == RIP_FMT_RGBA8 || fmt == RIP_FMT_BGRA8) ? 4 :
+                   (fmt == RIP_FMT_GRAY8 || fmt == RIP_FMT_NV12) ? 1 : 0;
     if (cn == 0) return false;
+    if (fmt == RIP_FMT_NV12 && (H & 1)) return false;
     const uintptr_t in_align = cn == 4 ? 15u : 3u;
     if ((reinterpret_cast<uintptr_t>(d_in) & in_align) || (reinterpret_cast<uintptr_t>(d_out) & 3u)) return false;
     if (getenv("RIP_DISABLE_FUSED")) return false;
@@ -143,12 +146,12 @@ static int pick_seg_rows(int out_rows, int n_frames, int n_band_groups, int devi
         const int v = atoi(e);
         if (v > 0) return v < out_rows ? v : out_rows;
     }
-    // enough blocks for >= ~3 waves of (SMs x resident blocks), but segments of >= 64 rows so the
-    // 6 warm-up rows stay below 10 %; never more than 256 rows (tail balance).  (Measured on 32 4K
-    // frames: 64 rows 440 us, 128 rows 416 us, 270 rows 415 us.)
+    // enough blocks for >= ~3 waves of (SMs x resident blocks), but segments of >= 32 rows (6 warm-up rows
+    // each); never more than 256 rows (tail balance).  Measured: 32 4K frames 94..270 rows 416-430 us (flat),
+    // 360 rows 500 us; a single 4K frame 32 rows 38 us, 64 rows 46 us, 128 rows 67 us.
     const long long target_blocks = (long long)sm_count(device) * resident_blocks * 3;
     int seg = 256;
-    while (seg > 64 && (long long)n_frames * n_band_groups * ((out_rows + seg - 1) / seg) < target_blocks) seg >>= 1;
+    while (seg > 32 && (long long)n_frames * n_band_groups * ((out_rows + seg - 1) / seg) < target_blocks) seg >>= 1;
     if (seg > out_rows) seg = out_rows;
     return seg;
 }
@@ -227,6 +230,7 @@ static int launch_fused_x2_n(cudaStream_t s, FusedParams p, int n_frames, int fm
     case RIP_FMT_BGR8:  launch_x2_t<NPX, 3, true>(with_blur, grid, s, xp); break;
     case RIP_FMT_RGBA8: launch_x2_t<NPX, 4, false>(with_blur, grid, s, xp); break;
     case RIP_FMT_BGRA8: launch_x2_t<NPX, 4, true>(with_blur, grid, s, xp); break;
+    case RIP_FMT_GRAY8: case RIP_FMT_NV12: launch_x2_t<NPX, 1, false>(with_blur, grid, s, xp); break;
     default: return fail(RIP_EINVAL, "rip_fused: unsupported input format %d", fmt);
     }
     RIP_LAUNCH_CHECK();
@@ -238,7 +242,7 @@ static int x2_npx(int W, int cn, const uint8_t *d_in, const uint8_t *d_out)
 {
     int want = 8;
     if (const char *e = getenv("RIP_FUSED_NPX")) want = atoi(e) == 4 ? 4 : 8;
-    const uintptr_t in_align8 = cn == 4 ? 15u : 7u;
+    const uintptr_t in_align8 = cn == 4 ? 15u : 7u;   // (1 and 3 channels: 8 pixels are 8 / 24 bytes, loaded as 64-bit words)
     const bool ok8 = (W & 7) == 0 && !(reinterpret_cast<uintptr_t>(d_in) & in_align8) && !(reinterpret_cast<uintptr_t>(d_out) & 7u);
     if (want == 8 && ok8) return 8;
     return 4;  // fused_supported() already guarantees W % 4 == 0 and the 4-pixel alignments
@@ -261,7 +265,9 @@ int launch_fused(cudaStream_t s, const uint8_t *d_in, uint8_t *d_out, int W, int
             return fail(RIP_EUNSUPPORTED, "rip_fused: weights are not a non-negative symmetric separable 5x5 kernel");
         memcpy(p.w, weights25, sizeof(float) * 25);
     }
-    const int cn = (fmt == RIP_FMT_RGB8 || fmt == RIP_FMT_BGR8) ? 3 : 4;
+    const int cn = (fmt == RIP_FMT_RGB8 || fmt == RIP_FMT_BGR8) ? 3 : (fmt == RIP_FMT_GRAY8 || fmt == RIP_FMT_NV12) ? 1 : 4;
+    // whole NV12 frames carry their chroma plane behind the luma plane; row bands are passed as plain luma rows
+    p.in_frame_bytes = (fmt == RIP_FMT_NV12 && in_row0 == 0 && in_rows == H) ? (size_t)W * H * 3 / 2 : (size_t)in_rows * W * cn;
     if (x2_npx(W, cn, d_in, d_out) == 8) return launch_fused_x2_n<8>(s, p, n_frames, fmt, with_blur, band, g, device);
     return launch_fused_x2_n<4>(s, p, n_frames, fmt, with_blur, band, g, device);
 }

@@ -73,6 +73,16 @@ template <int NPX, int CN, bool BGR>
 __device__ __forceinline__ uint32_t gray_x2(const uint32_t *w, u64 *Q, u64 *E)
 {
     constexpr int NP = NPX / 2;
+    if constexpr (CN == 1) {
+        // the input IS the gray image (GRAY8, or the luma plane of NV12): isolate the bytes; an isolated byte is
+        // already the integer bit pattern the later stages consume.  No exactness cases here.
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            Q[j] = pk2u(__byte_perm(w[j / 4], 0u, 0x4440u | (uint32_t)(j & 3)), __byte_perm(w[(j + NP) / 4], 0u, 0x4440u | (uint32_t)((j + NP) & 3)));
+            E[j] = 0ull;
+        }
+        return 0u;
+    } else {
     constexpr uint32_t cA = BGR ? 114u : 299u, cB = 587u, cC = BGR ? 299u : 114u;  // weights of byte 0,1,2
     constexpr uint32_t AB = cA | (cB << 16), C0 = cC, zA = cA << 16, BC = cB | (cC << 16);
     uint32_t t[NPX];
@@ -100,6 +110,7 @@ __device__ __forceinline__ uint32_t gray_x2(const uint32_t *w, u64 *Q, u64 *E)
         any |= lo2u(E[j]) | hi2u(E[j]);
     }
     return any;
+    }
 }
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
@@ -194,7 +205,12 @@ template <int NPX, int CN>
 __device__ __forceinline__ void load_row_x2(RawX<NPX, CN> &r, const uint8_t *p)
 {
     constexpr int NW = NPX * CN / 4;
-    if constexpr (NW == 3) {
+    if constexpr (NW == 1) {
+        r.w[0] = __ldg(reinterpret_cast<const uint32_t *>(p));
+    } else if constexpr (NW == 2) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2 *>(p));
+        r.w[0] = a.x; r.w[1] = a.y;
+    } else if constexpr (NW == 3) {
         const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
         r.w[0] = __ldg(q); r.w[1] = __ldg(q + 1); r.w[2] = __ldg(q + 2);
     } else if constexpr (NW == 4) {
@@ -334,7 +350,7 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
             for (int j = 0; j < NP; j++) sts_b64(pairs + 8 * j, Q[j]);
         }
 #ifndef RIP_X2_NOCOLD   // (experiment switch: hot path only, wrong results)
-        if (__builtin_expect(__any_sync(FULL, flagged), 0)) {
+        if (CN != 1 && __builtin_expect(__any_sync(FULL, flagged), 0)) {
             if (flagged) {
                 if constexpr (!BLUR) {
 #pragma unroll
@@ -549,7 +565,8 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     __shared__ float w25s[32];
     __shared__ __align__(16) float scratch[kWarpsPerBlock * 32];
     __shared__ uint32_t gray_down_s[2048];   // the (r,g) bit table of the gray fix: global-memory latency would stall the whole warp
-    for (int i = threadIdx.x; i < 2048; i += kWarpsPerBlock * 32) gray_down_s[i] = d_gray_down[i];
+    if constexpr (CN != 1)
+        for (int i = threadIdx.x; i < 2048; i += kWarpsPerBlock * 32) gray_down_s[i] = d_gray_down[i];
     if (threadIdx.x < 25) w25s[threadIdx.x] = p.w[threadIdx.x] * 1.2676506002282294e30f;   // * 2^100 (exact), see blur_replay_warp
     __syncthreads();  // the only block-level barrier: the warps are independent from here on
 
@@ -583,7 +600,7 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     geo.r_store = ys + HALO;
     geo.r_last = ye - 1 + HALO;
     geo.in_pitch = (uint32_t)W * CN;
-    const uint8_t *in_base = p.in + (size_t)frame * p.in_rows * geo.in_pitch;
+    const uint8_t *in_base = p.in + (size_t)frame * p.in_frame_bytes;
     geo.store_lane = ((geo.lane >= 1) && (geo.lane <= 30) && in_img) ? 1u : 0u;
 
     WarpX<NPX, CN> st;

@@ -192,6 +192,29 @@ def test_sobel_colour_input(ctx, oracle, shape, fmt, cn, npx, monkeypatch):
     _eq(ctx.process(img, rip.OP_EDGE, fmt), oracle.sobel(g), f"sobel colour {shape} cn={cn}")
 
 
+@pytest.mark.parametrize("shape", [(2, 8), (5, 12), (37, 120), (64, 128), (33, 244), (75, 75), (40, 496), (70, 720)])
+@pytest.mark.parametrize("npx", [8, 4])
+def test_gray_and_nv12_input_edge_and_fused(ctx, oracle, shape, npx, monkeypatch):
+    """GRAY8 frames, and NV12 frames whose luma plane is the image: Sobel and blur->Sobel on the
+    given gray, through the fused kernel where the shape allows it and the staged kernels elsewhere."""
+    monkeypatch.setenv("RIP_FUSED_NPX", str(npx))
+    h, w = shape
+    n = 3
+    rng = np.random.default_rng(77)
+    gray = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    wts = rip.gauss_weights(5, 1.0)
+    want_edge = np.stack([oracle.sobel(g) for g in gray])
+    want_fused = np.stack([oracle.sobel(oracle.blur(g, 5, weights=wts, threads=0)) for g in gray])
+    _eq(ctx.process(gray, rip.OP_EDGE, rip.FMT_GRAY8), want_edge, f"sobel GRAY8 {shape}")
+    _eq(ctx.process(gray, rip.OP_FUSED, rip.FMT_GRAY8, ksize=5, weights=wts), want_fused, f"fused GRAY8 {shape}")
+    if h % 2 == 0 and w % 4 == 0:
+        nv12 = np.concatenate([gray, rng.integers(0, 256, (n, h // 2, w), dtype=np.uint8)], axis=1)   # chroma: noise, never read
+        _eq(ctx.process(nv12, rip.OP_EDGE, rip.FMT_NV12), want_edge, f"sobel NV12 {shape}")
+        _eq(ctx.process(nv12, rip.OP_FUSED, rip.FMT_NV12, ksize=5, weights=wts), want_fused, f"fused NV12 {shape}")
+        with pytest.raises(rip.RipError):
+            ctx.process(nv12, rip.OP_GRAY, rip.FMT_NV12)
+
+
 def test_sobel_config3_1080p_batch(ctx, oracle):
     n = 8  # batch 64 in the bench; 8 distinct frames here, frame independence checked below
     frames = np.stack([synth_frame("uniform", 1080, 1920, 0xB200 + 3000 + i) for i in range(n)])

@@ -19,6 +19,7 @@ ap.add_argument("--w", type=int, default=3840)
 ap.add_argument("--h", type=int, default=2160)
 ap.add_argument("--launches", type=int, default=4)
 ap.add_argument("--kind", default="uniform")
+ap.add_argument("--fmt", default="rgb", help="rgb | gray | nv12 (gray / nv12: the input is the luma plane)")
 a = ap.parse_args()
 
 rng = np.random.default_rng(1)
@@ -26,15 +27,20 @@ if a.kind == "uniform":
     one = rng.integers(0, 256, (a.h, a.w, 3), dtype=np.uint8)
 else:
     one = np.full((a.h, a.w, 3), 77, np.uint8)
+if a.fmt == "gray":
+    one = np.ascontiguousarray(one[..., 0])
+elif a.fmt == "nv12":
+    one = np.ascontiguousarray(np.concatenate([one[..., 0], one[: a.h // 2, :, 1]], axis=0))
+FMT = {"rgb": rip.FMT_RGB8, "gray": rip.FMT_GRAY8, "nv12": rip.FMT_NV12}[a.fmt]
 frames = np.stack([np.roll(one, i, axis=1) for i in range(a.frames)])
 d_in = rip.DeviceBuffer(frames.nbytes).upload(frames)
 d_out = rip.DeviceBuffer(a.frames * a.h * a.w * 4)
 w = rip.gauss_weights(5, 1.0)
 def launch():
     if a.op == "fused":
-        rip.fused_dev(d_in.ptr, d_out.ptr, a.w, a.h, a.frames, rip.FMT_RGB8, 5, w)
+        rip.fused_dev(d_in.ptr, d_out.ptr, a.w, a.h, a.frames, FMT, 5, w)
     elif a.op == "sobel":
-        rip.sobel_dev(d_in.ptr, d_out.ptr, a.w, a.h, a.frames, rip.FMT_RGB8)
+        rip.sobel_dev(d_in.ptr, d_out.ptr, a.w, a.h, a.frames, FMT)
     elif a.op == "gray":
         rip.gray_dev(d_in.ptr, d_out.ptr, a.w, a.h, a.frames, rip.FMT_RGB8)
 
@@ -52,4 +58,4 @@ times.sort()
 ns = times[len(times) // 2]
 px = a.frames * a.h * a.w
 print(f"{a.op} {a.frames}x{a.w}x{a.h}: median {ns/1e3:.1f} us (min {times[0]/1e3:.1f}, max {times[-1]/1e3:.1f}, n={len(times)}), "
-      f"{px/ns*1e3:.0f} Mpx/s, {px*4/ns:.0f} GB/s algorithmic")
+      f"{px/ns*1e3:.0f} Mpx/s, {px*(4 if a.fmt == 'rgb' else 2)/ns:.0f} GB/s algorithmic")
