@@ -310,6 +310,24 @@ def test_fused_8_and_4_pixel_kernels_agree(oracle, monkeypatch):
     _eq(outs[1], want, "4 pixels per lane")
 
 
+@pytest.mark.parametrize("sigma", [1.0, 1.5])
+def test_fused_flat_regions_take_the_constant_window_shortcut(ctx, oracle, sigma):
+    """Letterbox bars / clipped highlights: whole warp-rows of constant gray settle through the host-evaluated
+    table of the reference's constant-window sums (sigma 1.5: 255 blurs to 254) and must still be exact, also
+    where a flat region meets texture."""
+    w = rip.gauss_weights(5, sigma)
+    h, wd = 96, 1024
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (h, wd, 3), dtype=np.uint8)
+    img[:30] = 0                      # black bar
+    img[30:52] = 255                  # clipped white
+    img[52:70, :600] = (200, 200, 200)  # a grey slab next to noise (every r=g=b triple is a multiple of 1000)
+    img[70:, 300:] = (13, 200, 77)
+    _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w, threads=0), f"flat regions sigma {sigma}")
+    g = np.ascontiguousarray(img[..., 1])
+    _eq(ctx.process(g, rip.OP_FUSED, rip.FMT_GRAY8, ksize=5, weights=w), oracle.sobel(oracle.blur(g, 5, weights=w, threads=0)), "flat regions, gray input")
+
+
 def test_fused_guard_band_statistics():
     """The exact replay must actually trigger (flat frames: always) yet stay rare on noise."""
     w = rip.gauss_weights(5, 1.0)

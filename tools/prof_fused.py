@@ -25,6 +25,8 @@ a = ap.parse_args()
 rng = np.random.default_rng(1)
 if a.kind == "uniform":
     one = rng.integers(0, 256, (a.h, a.w, 3), dtype=np.uint8)
+elif a.kind == "zero":
+    one = np.zeros((a.h, a.w, 3), np.uint8)
 else:
     one = np.full((a.h, a.w, 3), 77, np.uint8)
 if a.fmt == "gray":

@@ -58,7 +58,7 @@ while i < len(body):
     if op.startswith("VOTE"):
         prev_vote_recent = True
         vote_at = i
-    elif "prev_vote_recent" in dir() and prev_vote_recent and i - vote_at > 12:
+    elif "prev_vote_recent" in dir() and prev_vote_recent and i - vote_at > 40:
         prev_vote_recent = False
     if "prev_vote_recent" not in dir():
         prev_vote_recent = False
