@@ -311,10 +311,9 @@ def test_fused_8_and_4_pixel_kernels_agree(oracle, monkeypatch):
 
 
 @pytest.mark.parametrize("sigma", [1.0, 1.5])
-def test_fused_flat_regions_take_the_constant_window_shortcut(ctx, oracle, sigma):
-    """Letterbox bars / clipped highlights: whole warp-rows of constant gray settle through the host-evaluated
-    table of the reference's constant-window sums (sigma 1.5: 255 blurs to 254) and must still be exact, also
-    where a flat region meets texture."""
+def test_fused_flat_regions_are_exact(ctx, oracle, sigma):
+    """Letterbox bars / clipped highlights: every pixel of a constant region lies inside the guard band and is
+    replayed (sigma 1.5: 255 blurs to 254); results must be exact there and where a flat region meets texture."""
     w = rip.gauss_weights(5, sigma)
     h, wd = 96, 1024
     rng = np.random.default_rng(9)
