@@ -26,7 +26,7 @@
 //     followed by I2IP.U8.S32.SAT, which also packs the bytes.
 //   * a lane owns NPX horizontally adjacent pixels, pixel j paired with pixel j+NPX/2 in one 64-bit
 //     register so that every horizontal tap of a pair is again an aligned pair; the row loop is
-//     unrolled by 3 over three input-row buffers (loads run three rows ahead), so the buffer rotation
+//     unrolled by NB over NB input-row buffers (loads run NB rows ahead; 3, or 6 without the blur stage), so the buffer rotation
 //     and the two-row Sobel delay line are register renames, not moves.
 //
 // Included by rip_fused.cu inside its anonymous namespace (shares FusedParams, the gray table and the
@@ -317,7 +317,7 @@ __device__ __forceinline__ void blur_replay_warp(const u64 *F, uint32_t patch, u
 }
 
 // One image row of the sliding window: consumes the input row held in `buf` (row r, clamped to the
-// rows of the band), refills `buf` with row r + 3, and -- for r_store <= r <= r_last -- stores output
+// rows of the band), refills `buf` with row r + NB (NB = row buffers, see X2Cfg), and -- for r_store <= r <= r_last -- stores output
 // row r - HALO.  The border rules are applied at run time (per-lane selects in x, two rare uniform
 // branches in y), so this is the only copy of the row body; the caller unrolls it by three with three
 // row buffers, which makes the buffer rotation and the two-row Sobel delay line register renames.
@@ -335,7 +335,7 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
     const int W = p.W, H = p.H;
     (void)H;
 
-    // ---- 1. gray of row r; refill the buffer with row r + 3 ---------------------------------------
+    // ---- 1. gray of row r; refill the buffer with row r + NB --------------------------------------
     u64 Q[NP];
     {
         u64 E[NP];
@@ -521,33 +521,44 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
 
 // The rows of one segment.  Head: the warm-up rows and the first storing row (it may be frame row 0), one row
 // per trip with the SPECIAL copy of the row body and an explicit rotation of the three row buffers.  Main loop:
-// three rows per trip with the plain copy; the buffer rotation and the Sobel delay line are register renames
+// NB rows per trip with the plain copy; the buffer rotation and the Sobel delay line are register renames
 // there.  Tail: the remaining rows (the last may be frame row H-1), SPECIAL again.  Only the main loop is hot,
 // so only its three copies of the row body need to stay in the instruction cache.
-template <int NPX, int CN, bool BGR, bool BLUR, bool EDGE>
-__device__ __forceinline__ void run_rows_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &b0, RawX<NPX, CN> &b1, RawX<NPX, CN> &b2,
-                                            const X2Params &xp, GeoX &geo, int r)
+// NB = row buffers = how many rows ahead of their use the register loads run (and the unroll of the main loop:
+// 3 with the blur stage; 6 without it, where a row is consumed twice as fast and load latency is the top stall).
+template <int NPX, int CN, bool BGR, bool BLUR>
+struct X2Cfg {
+    static constexpr int NB = BLUR ? 3 : 6;
+};
+
+template <int NPX, int CN, bool BGR, bool BLUR, bool EDGE, int NB>
+__device__ __forceinline__ void run_rows_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> (&b)[NB], const X2Params &xp, GeoX &geo, int r)
 {
     const FusedParams &p = xp.f;
 #pragma unroll 1
     for (; r <= geo.r_store && r < geo.r_last; r++) {
-        step_x2<NPX, CN, BGR, BLUR, true, EDGE>(st, b0, xp, geo, r);
-        const RawX<NPX, CN> t = b0; b0 = b1; b1 = b2; b2 = t;
+        step_x2<NPX, CN, BGR, BLUR, true, EDGE>(st, b[0], xp, geo, r);
+        const RawX<NPX, CN> t = b[0];
+#pragma unroll
+        for (int k = 0; k + 1 < NB; k++) b[k] = b[k + 1];
+        b[NB - 1] = t;
     }
-    // the main loop runs while all three rows of a trip store, and the row they load (three ahead) as well as
-    // the line they prefetch (RIP_X2_L2PF further) lie inside the band: step s advances freely iff
-    // s + 2 + RIP_X2_L2PF < in_row0 + in_rows - 1
-    const int r_main_last = min(geo.r_last - 1, p.in_row0 + p.in_rows - 4 - RIP_X2_L2PF);
+    // the main loop runs while all rows of a trip store, and the row they load (NB ahead) as well as the line
+    // they prefetch (RIP_X2_L2PF further) lie inside the band: step s advances freely iff
+    // s + NB - 1 + RIP_X2_L2PF < in_row0 + in_rows - 1
+    const int r_main_last = min(geo.r_last - 1, p.in_row0 + p.in_rows - 1 - NB - RIP_X2_L2PF);
 #pragma unroll 1
-    for (; r + 2 <= r_main_last; r += 3) {
-        step_x2<NPX, CN, BGR, BLUR, false, EDGE>(st, b0, xp, geo, r);
-        step_x2<NPX, CN, BGR, BLUR, false, EDGE>(st, b1, xp, geo, r + 1);
-        step_x2<NPX, CN, BGR, BLUR, false, EDGE>(st, b2, xp, geo, r + 2);
+    for (; r + NB - 1 <= r_main_last; r += NB) {
+#pragma unroll
+        for (int k = 0; k < NB; k++) step_x2<NPX, CN, BGR, BLUR, false, EDGE>(st, b[k], xp, geo, r + k);
     }
 #pragma unroll 1
     for (; r <= geo.r_last; r++) {
-        step_x2<NPX, CN, BGR, BLUR, true, EDGE>(st, b0, xp, geo, r);
-        const RawX<NPX, CN> t = b0; b0 = b1; b1 = b2; b2 = t;
+        step_x2<NPX, CN, BGR, BLUR, true, EDGE>(st, b[0], xp, geo, r);
+        const RawX<NPX, CN> t = b[0];
+#pragma unroll
+        for (int k = 0; k + 1 < NB; k++) b[k] = b[k + 1];
+        b[NB - 1] = t;
     }
 }
 
@@ -612,17 +623,16 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     // (GaussianBlur.cpp:241) is actually exercised; other clamped rows are read-ahead only.
     int r = ys - HALO;
     const uint32_t xoff = in_img ? (uint32_t)x * CN : 0u;
-    RawX<NPX, CN> b0, b1, b2;   // rows r, r+1, r+2
-    {
-        const int i0 = min(max(r - p.in_row0, 0), p.in_rows - 1), i1 = min(max(r + 1 - p.in_row0, 0), p.in_rows - 1),
-                  i2 = min(max(r + 2 - p.in_row0, 0), p.in_rows - 1);
-        load_row_x2<NPX, CN>(b0, in_base + (size_t)i0 * geo.in_pitch + xoff);
-        load_row_x2<NPX, CN>(b1, in_base + (size_t)i1 * geo.in_pitch + xoff);
-        geo.src = in_base + (size_t)i2 * geo.in_pitch + xoff;
-        load_row_x2<NPX, CN>(b2, geo.src);
+    constexpr int NB = X2Cfg<NPX, CN, BGR, BLUR>::NB;
+    RawX<NPX, CN> b[NB];   // rows r .. r + NB - 1
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+        const int i = min(max(r + k - p.in_row0, 0), p.in_rows - 1);
+        geo.src = in_base + (size_t)i * geo.in_pitch + xoff;
+        load_row_x2<NPX, CN>(b[k], geo.src);
     }
-    // step r loads row r + 3 = one past the row src points at: advance iff in_row0 <= r + 2 < in_row0 + in_rows - 1
-    geo.adv_lo = p.in_row0 - 2;
+    // step r loads row r + NB = one past the row src points at: advance iff in_row0 <= r + NB - 1 < in_row0 + in_rows - 1
+    geo.adv_lo = p.in_row0 - (NB - 1);
     geo.adv_n = p.in_rows - 1;
     {   // lanes 0..n-1 fetch the n consecutive 128-byte lines that hold the warp's NPX*CN*32 bytes of a row
         constexpr int kLines = (32 * NPX * CN + 127) / 128 + 1;
@@ -639,9 +649,9 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     // cache (no_instruction stalls 0.17 -> 1.86 warps per issue).  RIP_X2_INTERIOR re-enables it for experiments
     // (the vote tells the compiler what it cannot see: the choice is the same in every lane).
 #ifdef RIP_X2_INTERIOR
-    if (__any_sync(FULL, band == 0 || lane_last <= 31)) run_rows_x2<NPX, CN, BGR, BLUR, true>(st, b0, b1, b2, xp, geo, r);
-    else run_rows_x2<NPX, CN, BGR, BLUR, false>(st, b0, b1, b2, xp, geo, r);
+    if (__any_sync(FULL, band == 0 || lane_last <= 31)) run_rows_x2<NPX, CN, BGR, BLUR, true, NB>(st, b, xp, geo, r);
+    else run_rows_x2<NPX, CN, BGR, BLUR, false, NB>(st, b, xp, geo, r);
 #else
-    run_rows_x2<NPX, CN, BGR, BLUR, true>(st, b0, b1, b2, xp, geo, r);
+    run_rows_x2<NPX, CN, BGR, BLUR, true, NB>(st, b, xp, geo, r);
 #endif
 }
