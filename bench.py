@@ -201,6 +201,10 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # one process per GPU: host thread and pinned frame buffers on the GPU's own NUMA node (matters for the
+    # end-to-end leg at 8 GPUs, where every rank streams 50 GB/s from host memory)
+    numa = rip.bind_host_to_device_numa(dev) if world > 1 else {}
+
     L = rip.lib()
     weights = rip.gauss_weights(KSIZE, SIGMA)
     n = FRAMES_PER_GPU
@@ -288,7 +292,8 @@ def main() -> None:
             "e2e": {"value": e2e_mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": int(frames.nbytes) * world,
                     "d2h_bytes_per_step": int(n * H * W) * world, "steps": e2e_steps,
                     "frames_per_s": e2e_mpx * 1e6 / (W * H), "matches_resident_output": e2e_ok,
-                    "api": "rip_process_host (pinned host buffers, 3 chunk streams per device)"},
+                    "api": "rip_process_host (pinned host buffers, 3 chunk streams per device)",
+                    "host_numa_binding": numa or None},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

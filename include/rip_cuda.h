@@ -77,6 +77,10 @@ const char *rip_last_error_string(void);
 int rip_device_count(int *count);
 int rip_device_name(int device, char *buf, size_t buf_len);
 int rip_device_get_info(int device, rip_device_info *info);
+/* "domain:bus:device.function" of the device (cudaDeviceGetPCIBusId): lets a one-process-per-GPU launcher put its
+ * host thread and its pinned frame buffers on the NUMA node the GPU hangs off (/sys/bus/pci/devices/<id>/numa_node),
+ * which the end-to-end (host-buffer) throughput of an 8-GPU box depends on. */
+int rip_device_pci_bus_id(int device, char *buf, size_t buf_len);
 
 /* ---- context / program / kernel handles (replace clCreateContext, clCreateProgramWithSource +
  *      clBuildProgram, clCreateKernel: RT/src/Controller.cpp:97-191).  The kernels are compiled

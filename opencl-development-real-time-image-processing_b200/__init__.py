@@ -29,6 +29,7 @@ CHANNELS = {FMT_GRAY8: 1, FMT_RGB8: 3, FMT_BGR8: 3, FMT_RGBA8: 4, FMT_BGRA8: 4, 
 # every symbol include/rip_cuda.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "rip_abi_version", "rip_last_error_string", "rip_device_count", "rip_device_name", "rip_device_get_info",
+    "rip_device_pci_bus_id",
     "rip_ctx_create", "rip_ctx_destroy", "rip_ctx_device_count", "rip_ctx_device",
     "rip_module_load", "rip_module_release", "rip_kernel_get", "rip_kernel_release", "rip_kernel_op",
     "rip_stream_create", "rip_stream_destroy", "rip_stream_sync", "rip_device_sync",
@@ -75,6 +76,7 @@ def lib() -> C.CDLL:
         "rip_last_error_string": ([], C.c_char_p),
         "rip_device_count": ([i32p], C.c_int),
         "rip_device_name": ([C.c_int, C.c_char_p, C.c_size_t], C.c_int),
+        "rip_device_pci_bus_id": ([C.c_int, C.c_char_p, C.c_size_t], C.c_int),
         "rip_device_get_info": ([C.c_int, C.POINTER(DeviceInfo)], C.c_int),
         "rip_ctx_create": ([i32p, C.c_int, C.POINTER(vp)], C.c_int),
         "rip_ctx_destroy": ([vp], C.c_int),
@@ -143,6 +145,34 @@ def device_info(device: int = 0) -> DeviceInfo:
     info = DeviceInfo()
     check(lib().rip_device_get_info(device, C.byref(info)), "rip_device_get_info")
     return info
+
+
+def bind_host_to_device_numa(device: int = 0) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, so that buffers pinned afterwards
+    (first touch) and the copy-issuing thread are local to it.  For one-process-per-GPU launchers; returns what it
+    did ({} when the topology cannot be read: containers without /sys, single-node hosts)."""
+    try:
+        buf = C.create_string_buffer(32)
+        check(lib().rip_device_pci_bus_id(device, buf, 32), "rip_device_pci_bus_id")
+        bdf = buf.value.decode().lower()
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(base + "/numa_node") as f:
+            node = int(f.read().strip())
+        with open(base + "/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return {}
+        os.sched_setaffinity(0, cpus)
+        return {"pci": bdf, "numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return {}
 
 
 def launch_count() -> int:

@@ -197,6 +197,14 @@ extern "C" int rip_device_get_info(int device, rip_device_info *info)
     return RIP_OK;
 }
 
+extern "C" int rip_device_pci_bus_id(int device, char *buf, size_t buf_len)
+{
+    if (int rc = check_device(device)) return rc;
+    if (!buf || buf_len < 13) return fail(RIP_EINVAL, "rip_device_pci_bus_id: buffer of at least 13 bytes needed");
+    RIP_CUDA(cudaDeviceGetPCIBusId(buf, (int)buf_len, device));
+    return RIP_OK;
+}
+
 extern "C" int rip_device_name(int device, char *buf, size_t buf_len)
 {
     if (!buf || buf_len == 0) return fail(RIP_EINVAL, "rip_device_name: NULL buffer");
