@@ -65,7 +65,7 @@ struct FusedParams {
 // the three double products decides between q and q-1; since 114*b mod 1000 has period 500 > 255, (r,g)
 // determines that b uniquely, so one bit per (r,g) -- tabulated on the host by evaluating the reference
 // expression itself -- says whether the result is q-1.
-__device__ uint32_t d_gray_down[2048];  // bit (r<<8|g): the double evaluation lands below q
+__device__ __align__(16) uint32_t d_gray_down[2048];  // bit (r<<8|g): the double evaluation lands below q
 
 __device__ __forceinline__ float sqrt_approx(float x)
 {

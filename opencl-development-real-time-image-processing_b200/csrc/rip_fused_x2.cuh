@@ -575,9 +575,18 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     __shared__ __align__(16) uint32_t patch[kWarpsPerBlock * 3 * kRowW];   // per lane: NPX/2 pairs at a 16-byte stride + NPX words of raw input
     __shared__ float w25s[32];
     __shared__ __align__(16) float scratch[kWarpsPerBlock * 32];
-    __shared__ uint32_t gray_down_s[2048];   // the (r,g) bit table of the gray fix: global-memory latency would stall the whole warp
-    if constexpr (CN != 1)
-        for (int i = threadIdx.x; i < 2048; i += kWarpsPerBlock * 32) gray_down_s[i] = d_gray_down[i];
+    __shared__ __align__(16) uint32_t gray_down_s[2048];   // the (r,g) bit table of the gray fix: global-memory latency would stall the whole warp
+    if constexpr (CN != 1) {
+        // 8 KB per block: all loads of a thread in flight at once (a dependent load/store loop here was 3.9 % of
+        // the kernel's stall samples: sixteen L2 round trips in sequence before the first row)
+        static_assert(2048 % (4 * kWarpsPerBlock * 32) == 0, "table copy is unrolled");
+        constexpr int kPer = 2048 / (4 * kWarpsPerBlock * 32);
+        uint4 t[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; k++) t[k] = __ldg(reinterpret_cast<const uint4 *>(d_gray_down) + threadIdx.x + k * kWarpsPerBlock * 32);
+#pragma unroll
+        for (int k = 0; k < kPer; k++) reinterpret_cast<uint4 *>(gray_down_s)[threadIdx.x + k * kWarpsPerBlock * 32] = t[k];
+    }
     if (threadIdx.x < 25) w25s[threadIdx.x] = p.w[threadIdx.x] * 1.2676506002282294e30f;   // * 2^100 (exact), see blur_replay_warp
     __syncthreads();  // the only block-level barrier: the warps are independent from here on
 
