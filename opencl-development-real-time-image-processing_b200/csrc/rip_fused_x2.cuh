@@ -394,6 +394,15 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
             st.a2[j] = fma2(GV1, Q[j], st.a3[j]);
             st.a3[j] = mul2(GV2, Q[j]);
         }
+        if constexpr (SPECIAL) {
+            // warm-up rows of a segment: the first blurred row any stored output reads (ys - 1) completes at step
+            // r_store - 2; before that only the vertical accumulators matter (the vote tells the compiler that
+            // the whole warp leaves together)
+            if (__all_sync(FULL, r < geo.r_store - 2)) {
+                geo.dst += W;
+                return;
+            }
+        }
         // horizontal pass: P[k] = (c[k], c[k + NP]) with c[m] = V of pixel m - 2 (pixel m lives in
         // pair m % NP, half m / NP).  Clamp-to-edge columns (GaussianBlur.cpp:240): V is linear in the
         // gray column, so the clamp applies to V: left of column 0 / right of column W-1 repeat it.
