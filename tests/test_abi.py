@@ -75,3 +75,16 @@ def test_product_never_links_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert "rip_oracle" not in txt and "import oracle" not in txt, os.path.join(dirpath, fn)
+
+
+def test_numa_binding_helper_is_harmless_without_a_gpu():
+    """bind_host_to_device_numa() must never raise: it returns {} when the device or the topology cannot be read."""
+    import os
+    import rip_b200 as rip
+    before = os.sched_getaffinity(0)
+    info = rip.bind_host_to_device_numa(0)
+    assert isinstance(info, dict)
+    if not info:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, before)
