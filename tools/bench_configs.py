@@ -98,6 +98,43 @@ one = rng.integers(0, 256, (4320, 7680, 3), dtype=np.uint8)
 d_in, d_out = dev_buf(one), rip.DeviceBuffer(4320 * 7680)
 us, best = timed(lambda: rip.fused_dev(d_in.ptr, d_out.ptr, 7680, 4320, 1, rip.FMT_RGB8, 5, w))
 row("config 5  fused 7680x4320 RGB8, 1 frame, whole frame on 1 GPU (fits L2)", us, best, 7680 * 4320, 4)
+del d_in, d_out
+# config 5: throughput over a batch of 16 8K frames resident on one GPU (2.1 GB in)
+d_in, d_out = rip.DeviceBuffer(16 * one.nbytes), rip.DeviceBuffer(16 * 4320 * 7680)
+for i in range(16):
+    d_in.upload(np.roll(one, 17 * i, axis=1), offset=i * one.nbytes)
+us, best = timed(lambda: rip.fused_dev(d_in.ptr, d_out.ptr, 7680, 4320, 16, rip.FMT_RGB8, 5, w), n=9)
+row("config 5  fused 7680x4320 RGB8, batch 16 on 1 GPU", us, best, 16 * 7680 * 4320, 4)
+del d_in, d_out
+# camera-format input: NV12 frames, the luma plane is the image (2 algorithmic bytes per pixel)
+nv = rng.integers(0, 256, (32, 2160 * 3 // 2, 3840), dtype=np.uint8)
+d_in, d_out = dev_buf(nv), rip.DeviceBuffer(32 * 3840 * 2160)
+us, best = timed(lambda: rip.fused_dev(d_in.ptr, d_out.ptr, 3840, 2160, 32, rip.FMT_NV12, 5, w))
+row("          fused 5x5->Sobel on NV12 3840x2160 (luma plane), 32 frames", us, best, 32 * 3840 * 2160, 2)
+us, best = timed(lambda: rip.sobel_dev(d_in.ptr, d_out.ptr, 3840, 2160, 32, rip.FMT_NV12))
+row("          Sobel on NV12 3840x2160 (luma plane), 32 frames", us, best, 32 * 3840 * 2160, 2)
+del d_in, d_out, nv
+# informational CPU rows for config 3 (one 1080p frame): the genuine OpenCV calls of EdgeDetection.cpp:231-240
+# where Python cv2 is installed, and the oracle port, single thread
+try:
+    import cv2
+    g1080 = rng.integers(0, 256, (1080, 1920), dtype=np.uint8)
+    kx = np.array([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], np.float32)
+    cv2.setNumThreads(1)
+    def cv_sobel():
+        gx = cv2.filter2D(g1080, cv2.CV_32F, kx)
+        gy = cv2.filter2D(g1080, cv2.CV_32F, kx.T.copy())
+        m = cv2.magnitude(gx, gy)
+        return m.round().clip(0, 255).astype(np.uint8)
+    cv_sobel()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        cv_sobel()
+    dt = (time.perf_counter() - t0) / 5
+    print(f"config 3  (CPU, informational) cv2 {cv2.__version__} filter2D x2 + magnitude on one 1920x1080 gray frame, 1 thread: "
+          f"{dt * 1e3:.2f} ms ({1920 * 1080 / dt / 1e6:.0f} Mpx/s)")
+except Exception as e:  # noqa: BLE001
+    print(f"config 3  (CPU, informational) cv2 not available: {e}")
 # row bands through the host pipeline (H2D of band + halo, kernel, D2H), 1..N GPUs: wall-clock latency
 pin = rip.PinnedBuffer(one.nbytes)
 pin.array[:] = one.reshape(-1)
