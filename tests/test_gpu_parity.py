@@ -139,6 +139,24 @@ def test_blur_separable_kernel_equals_exact_kernel_and_oracle(ctx, oracle, k, si
             f"separable blur gray K={k} frame {i}")
         monkeypatch.setenv("RIP_BLUR_EXACT", "1")
         _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), want, f"exact blur K={k} frame {i}")
+        if k == 5:   # 5x5 RGBA has two guard-band kernels: streaming (large inputs) and tiled; force each
+            monkeypatch.delenv("RIP_BLUR_EXACT", raising=False)
+            for force in ("RIP_BLUR_TILED", "RIP_BLUR_STREAM"):
+                monkeypatch.setenv(force, "1")
+                _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), want, f"{force} blur frame {i}")
+                monkeypatch.delenv(force, raising=False)
+
+
+@pytest.mark.parametrize("shape", [(3, 130, 250), (2, 67, 61), (1, 40, 1000), (5, 33, 64)])
+def test_blur_streaming_kernel_batches_and_ragged_widths(ctx, oracle, shape, monkeypatch):
+    monkeypatch.setenv("RIP_BLUR_STREAM", "1")
+    n, h, wd = shape
+    for sigma in (1.0, 1.5):
+        w = rip.gauss_weights(5, sigma)
+        imgs = np.stack([synth_frame("uniform" if i % 2 == 0 else "smooth", h, wd, 40 + i, 4) for i in range(n)])
+        got = ctx.process(imgs, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=5, weights=w)
+        for i in range(n):
+            _eq(got[i], oracle.blur(imgs[i], 5, weights=w, threads=0), f"streaming blur {shape} sigma {sigma} frame {i}")
 
 
 def test_blur_guard_band_statistics_and_non_separable_weights(ctx, oracle):
