@@ -34,6 +34,9 @@
 #ifndef RIP_X2_MINB8
 #define RIP_X2_MINB8 4
 #endif
+#ifndef RIP_X2_MINB8_NOBLUR
+#define RIP_X2_MINB8_NOBLUR 5   // colour -> gray -> Sobel: five blocks (20 warps) per SM (config 3: 127 -> 123 us; gray input is better off with 4)
+#endif
 #ifndef RIP_X2_MINB4
 #define RIP_X2_MINB4 6
 #endif

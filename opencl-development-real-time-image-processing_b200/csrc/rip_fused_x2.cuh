@@ -572,7 +572,7 @@ __device__ __forceinline__ void run_rows_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> (&
 }
 
 template <int NPX, int CN, bool BGR, bool BLUR>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, NPX == 8 ? RIP_X2_MINB8 : RIP_X2_MINB4)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, NPX == 8 ? ((BLUR || CN == 1) ? RIP_X2_MINB8 : RIP_X2_MINB8_NOBLUR) : RIP_X2_MINB4)
 fused_x2_kernel(const __grid_constant__ X2Params xp)
 {
     constexpr int HALO = BLUR ? 3 : 1;  // input rows above/below an output row
