@@ -107,17 +107,19 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[k][j] = 0ull;
 
-    // source rows: clamp to the image (GaussianBlur.cpp:241), then to the rows the band holds (read-ahead only)
-    auto row_ptr = [&](int r) {
-        const int rr = min(max(min(max(r, 0), p.H - 1) - p.src_row0, 0), p.src_rows - 1);
-        return reinterpret_cast<const uint32_t *>(fsrc + (size_t)rr * p.W * 4);
-    };
-    uint32_t n0, n1;                 // the row loaded one step ahead
+    // source rows: clamp to the image (GaussianBlur.cpp:241), then to the rows the band holds (read-ahead only).
+    // The clamped index of row r + 1 is one more than that of row r iff row_lo <= r < row_hi, so the two
+    // per-lane pointers just advance under that test.
+    const int row_lo = max(0, p.src_row0), row_hi = min(p.H - 1, p.src_row0 + p.src_rows - 1);
+    const uint32_t row_span = (uint32_t)max(row_hi - row_lo, 0);
+    const uint32_t *pn0, *pn1;       // this lane's two pixels in the row loaded last
     {
-        const uint32_t *row = row_ptr(ys - 2);
-        n0 = __ldg(row + c0);
-        n1 = __ldg(row + c1);
+        const int rr = min(max(min(max(ys - 2, 0), p.H - 1) - p.src_row0, 0), p.src_rows - 1);
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(fsrc + (size_t)rr * p.W * 4);
+        pn0 = row + c0;
+        pn1 = row + c1;
     }
+    uint32_t n0 = __ldg(pn0), n1 = __ldg(pn1);   // the row loaded one step ahead
     uint32_t *orow = reinterpret_cast<uint32_t *>(fdst + (size_t)(ys - p.out_row0) * p.W * 4);
 
     // one row: PH = (r - (ys - 2)) mod 5; an output row lives in the slot of the phase at which it completes.
@@ -126,11 +128,12 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const __grid_constant__
     auto step = [&](auto ph_tag, int r) {
         constexpr int PH = decltype(ph_tag)::value;
         const uint32_t q0 = n0, q1 = n1;
-        {
-            const uint32_t *row = row_ptr(r + 1);
-            n0 = __ldg(row + c0);
-            n1 = __ldg(row + c1);
+        if ((uint32_t)(r - row_lo) < row_span) {   // row r + 1 is a new row (not a clamped repeat of row r)
+            pn0 += p.W;
+            pn1 += p.W;
         }
+        n0 = __ldg(pn0);
+        n1 = __ldg(pn1);
         // raw pixels into the ring (for the replay): ring slot = PH
         asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring + PH * 256u + 8u * lane), "r"(q0), "r"(q1) : "memory");
         const bs_u64 Q[4] = {bs_cvt2(q0, 0x7440, 0x7441), bs_cvt2(q0, 0x7442, 0x7443), bs_cvt2(q1, 0x7440, 0x7441), bs_cvt2(q1, 0x7442, 0x7443)};
