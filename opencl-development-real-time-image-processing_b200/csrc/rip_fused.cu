@@ -197,7 +197,8 @@ static int ensure_gray_table(int device)
 template <int NPX, int CN, bool BGR>
 static void launch_x2_t(bool blur, dim3 grid, cudaStream_t s, const X2Params &xp)
 {
-    if (blur) fused_x2_kernel<NPX, CN, BGR, true><<<grid, kWarpsPerBlock * 32, 0, s>>>(xp);
+    if (blur && xp.f.slow_counter) fused_x2_kernel<NPX, CN, BGR, true, true><<<grid, kWarpsPerBlock * 32, 0, s>>>(xp);   // (statistics build)
+    else if (blur) fused_x2_kernel<NPX, CN, BGR, true><<<grid, kWarpsPerBlock * 32, 0, s>>>(xp);
     else fused_x2_kernel<NPX, CN, BGR, false><<<grid, kWarpsPerBlock * 32, 0, s>>>(xp);
 }
 

@@ -263,7 +263,9 @@ struct GeoX {
 // fl(q*2^-149 * w*2^100) = fl(q * w) * 2^-49 exactly (same mantissa, results stay normal), likewise every
 // partial sum, so the scaled chain rounds exactly like the reference's and needs no integer-to-float
 // conversion.  Columns are clamped to [cmin, cmax] (clamp-to-edge, GaussianBlur.cpp:240).
-template <int NPX>
+// STATS: count the replayed pixels (rip_debug_slow_path_stats); a separate instantiation so that the production
+// kernel does not carry the counting code in its three copies of this block
+template <int NPX, bool STATS>
 __device__ __forceinline__ void blur_replay_warp(const u64 *F, uint32_t patch, uint32_t scratch, uint32_t ring_warp, uint32_t ring_cur,
                                                  uint32_t w25, int cmin, int cmax, uint32_t zoff, uint32_t zthr,
                                                  unsigned long long *slow_counter)
@@ -309,7 +311,9 @@ __device__ __forceinline__ void blur_replay_warp(const u64 *F, uint32_t patch, u
                 acc = __fadd_rn(acc, lds_f32(scratch + 4 * 24));
                 acc = __fmul_rn(acc, 562949953421312.0f);   // * 2^49: back to the reference's scale (exact)
                 sts_u32(patch + pair_off<NPX, 16>(j), __float_as_uint(kBias + truncf(fminf(fmaxf(acc, 0.f), 255.f))));
-                if (slow_counter) atomicAdd(slow_counter, 1ull);
+                if constexpr (STATS) {
+                    if (slow_counter) atomicAdd(slow_counter, 1ull);
+                }
             }
             __syncwarp();
         }
@@ -326,7 +330,7 @@ __device__ __forceinline__ void blur_replay_warp(const u64 *F, uint32_t patch, u
 //            line exist, BORDER_REFLECT_101 in y.  The main loop's copies check none of that.
 //   EDGE     the warp's band holds image column 0 and/or W-1: per-lane border selects in x.  Interior warps
 //            (most) run copies without them.
-template <int NPX, int CN, bool BGR, bool BLUR, bool SPECIAL, bool EDGE>
+template <int NPX, int CN, bool BGR, bool BLUR, bool SPECIAL, bool EDGE, bool STATS>
 __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, const X2Params &xp, GeoX &geo, int r)
 {
     constexpr int NP = NPX / 2;
@@ -440,7 +444,7 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
 #pragma unroll
             for (int j = 0; j < NP; j++) sts_b64(geo.patch + 16 * j, F[j]);
             __syncwarp();  // the newest ring row was just stored by the other lanes
-            blur_replay_warp<NPX>(F, geo.patch, geo.scratch, geo.ring_warp, geo.ring_cur, geo.w25, geo.cmin, geo.cmax, xp.zoff, xp.zthr,
+            blur_replay_warp<NPX, STATS>(F, geo.patch, geo.scratch, geo.ring_warp, geo.ring_cur, geo.w25, geo.cmin, geo.cmax, xp.zoff, xp.zthr,
                                   p.slow_counter);
             // (its trailing __syncwarp also orders the ring reads before the next step overwrites the oldest slot)
             reload_pairs_if<NP, 16>(F, geo.patch, flagged);
@@ -540,13 +544,13 @@ struct X2Cfg {
     static constexpr int NB = BLUR ? 3 : 6;
 };
 
-template <int NPX, int CN, bool BGR, bool BLUR, bool EDGE, int NB>
+template <int NPX, int CN, bool BGR, bool BLUR, bool EDGE, int NB, bool STATS>
 __device__ __forceinline__ void run_rows_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> (&b)[NB], const X2Params &xp, GeoX &geo, int r)
 {
     const FusedParams &p = xp.f;
 #pragma unroll 1
     for (; r <= geo.r_store && r < geo.r_last; r++) {
-        step_x2<NPX, CN, BGR, BLUR, true, EDGE>(st, b[0], xp, geo, r);
+        step_x2<NPX, CN, BGR, BLUR, true, EDGE, STATS>(st, b[0], xp, geo, r);
         const RawX<NPX, CN> t = b[0];
 #pragma unroll
         for (int k = 0; k + 1 < NB; k++) b[k] = b[k + 1];
@@ -559,11 +563,11 @@ __device__ __forceinline__ void run_rows_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> (&
 #pragma unroll 1
     for (; r + NB - 1 <= r_main_last; r += NB) {
 #pragma unroll
-        for (int k = 0; k < NB; k++) step_x2<NPX, CN, BGR, BLUR, false, EDGE>(st, b[k], xp, geo, r + k);
+        for (int k = 0; k < NB; k++) step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS>(st, b[k], xp, geo, r + k);
     }
 #pragma unroll 1
     for (; r <= geo.r_last; r++) {
-        step_x2<NPX, CN, BGR, BLUR, true, EDGE>(st, b[0], xp, geo, r);
+        step_x2<NPX, CN, BGR, BLUR, true, EDGE, STATS>(st, b[0], xp, geo, r);
         const RawX<NPX, CN> t = b[0];
 #pragma unroll
         for (int k = 0; k + 1 < NB; k++) b[k] = b[k + 1];
@@ -571,7 +575,7 @@ __device__ __forceinline__ void run_rows_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> (&
     }
 }
 
-template <int NPX, int CN, bool BGR, bool BLUR>
+template <int NPX, int CN, bool BGR, bool BLUR, bool STATS = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, NPX == 8 ? ((BLUR || CN == 1) ? RIP_X2_MINB8 : RIP_X2_MINB8_NOBLUR) : RIP_X2_MINB4)
 fused_x2_kernel(const __grid_constant__ X2Params xp)
 {
@@ -667,9 +671,9 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     // cache (no_instruction stalls 0.17 -> 1.86 warps per issue).  RIP_X2_INTERIOR re-enables it for experiments
     // (the vote tells the compiler what it cannot see: the choice is the same in every lane).
 #ifdef RIP_X2_INTERIOR
-    if (__any_sync(FULL, band == 0 || lane_last <= 31)) run_rows_x2<NPX, CN, BGR, BLUR, true, NB>(st, b, xp, geo, r);
-    else run_rows_x2<NPX, CN, BGR, BLUR, false, NB>(st, b, xp, geo, r);
+    if (__any_sync(FULL, band == 0 || lane_last <= 31)) run_rows_x2<NPX, CN, BGR, BLUR, true, NB, STATS>(st, b, xp, geo, r);
+    else run_rows_x2<NPX, CN, BGR, BLUR, false, NB, STATS>(st, b, xp, geo, r);
 #else
-    run_rows_x2<NPX, CN, BGR, BLUR, true, NB>(st, b, xp, geo, r);
+    run_rows_x2<NPX, CN, BGR, BLUR, true, NB, STATS>(st, b, xp, geo, r);
 #endif
 }
