@@ -274,10 +274,14 @@ __device__ __forceinline__ void blur_replay_warp(const u64 *F, uint32_t patch, u
     constexpr uint32_t kRowB = 32 * NPX * 4;
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t my = 0;   // this lane's pixels inside the guard band (bit j = pixel j)
+    // A pixel whose S~ is exactly 0 (bit pattern of kBias) needs no replay: the taps are non-negative, so every
+    // gray value under a non-zero tap is 0 and the reference's sum is 0 as well.  (Black bars would otherwise
+    // replay every pixel: 36x slower than textured content.)
+    const uint32_t kZero = __float_as_uint(kBias);
 #pragma unroll
     for (int j = 0; j < NP; j++) {
-        my |= (((lo2u(F[j]) << (32 - kFracBits)) + zoff) < zthr ? 1u : 0u) << j;
-        my |= (((hi2u(F[j]) << (32 - kFracBits)) + zoff) < zthr ? 1u : 0u) << (j + NP);
+        my |= ((((lo2u(F[j]) << (32 - kFracBits)) + zoff) < zthr && lo2u(F[j]) != kZero) ? 1u : 0u) << j;
+        my |= ((((hi2u(F[j]) << (32 - kFracBits)) + zoff) < zthr && hi2u(F[j]) != kZero) ? 1u : 0u) << (j + NP);
     }
     uint32_t lanes = __ballot_sync(FULL, my != 0u);
     // this lane's tap: ring row of ky (oldest row first: the slot after the newest), column offset, weight
