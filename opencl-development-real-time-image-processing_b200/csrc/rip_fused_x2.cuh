@@ -274,14 +274,10 @@ __device__ __forceinline__ void blur_replay_warp(const u64 *F, uint32_t patch, u
     constexpr uint32_t kRowB = 32 * NPX * 4;
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t my = 0;   // this lane's pixels inside the guard band (bit j = pixel j)
-    // A pixel whose S~ is exactly 0 (bit pattern of kBias) needs no replay: the taps are non-negative, so every
-    // gray value under a non-zero tap is 0 and the reference's sum is 0 as well.  (Black bars would otherwise
-    // replay every pixel: 36x slower than textured content.)
-    const uint32_t kZero = __float_as_uint(kBias);
 #pragma unroll
     for (int j = 0; j < NP; j++) {
-        my |= ((((lo2u(F[j]) << (32 - kFracBits)) + zoff) < zthr && lo2u(F[j]) != kZero) ? 1u : 0u) << j;
-        my |= ((((hi2u(F[j]) << (32 - kFracBits)) + zoff) < zthr && hi2u(F[j]) != kZero) ? 1u : 0u) << (j + NP);
+        my |= (((lo2u(F[j]) << (32 - kFracBits)) + zoff) < zthr ? 1u : 0u) << j;
+        my |= (((hi2u(F[j]) << (32 - kFracBits)) + zoff) < zthr ? 1u : 0u) << (j + NP);
     }
     uint32_t lanes = __ballot_sync(FULL, my != 0u);
     // this lane's tap: ring row of ky (oldest row first: the slot after the newest), column offset, weight
@@ -300,6 +296,10 @@ __device__ __forceinline__ void blur_replay_warp(const u64 *F, uint32_t patch, u
         while (m) {
             const uint32_t j = (uint32_t)__ffs(m) - 1u;
             m &= m - 1u;
+            // A pixel whose S~ is exactly 0 (bit pattern of kBias) needs no replay: the taps are non-negative, so
+            // every gray value under a non-zero tap is 0 and the reference's sum is 0 as well (black regions would
+            // otherwise pay ~100 instructions per pixel).  Every lane reads the owner's copy of F: uniform.
+            if (__all_sync(FULL, lds_u32(patch + (uint32_t)(((int)src - (int)lane) * (3 * NPX * 4)) + pair_off<NPX, 16>(j)) == __float_as_uint(kBias))) continue;
             const uint32_t cc = (uint32_t)min(max((int)(NPX * src + j) + dx, cmin), cmax);
             const uint32_t g = lds_u32(row + 4u * (cc & ~(uint32_t)(NPX - 1)) + pair_off<NPX, 8>(cc & (NPX - 1)));
             sts_u32(scratch + 4u * lane, __float_as_uint(__fmul_rn(__uint_as_float(g), wt)));
