@@ -279,6 +279,9 @@ __device__ __forceinline__ void blur_replay_warp(const u64 *F, uint32_t patch, u
         my |= (((lo2u(F[j]) << (32 - kFracBits)) + zoff) < zthr ? 1u : 0u) << j;
         my |= (((hi2u(F[j]) << (32 - kFracBits)) + zoff) < zthr ? 1u : 0u) << (j + NP);
     }
+    // of the two halo lanes only the pixel next to the band feeds an output (through the Sobel halo exchange)
+    if (lane == 0u) my &= 1u << (NPX - 1);
+    if (lane == 31u) my &= 1u;
     uint32_t lanes = __ballot_sync(FULL, my != 0u);
     // this lane's tap: ring row of ky (oldest row first: the slot after the newest), column offset, weight
     const uint32_t t = lane < 25u ? lane : 24u, ky = t / 5u, kx = t - 5u * ky;
