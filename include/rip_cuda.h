@@ -45,6 +45,7 @@ typedef struct rip_ctx rip_ctx;        /* device set + cached buffers; replaces 
 typedef struct rip_module rip_module;  /* loaded kernel image;  replaces cl_program */
 typedef struct rip_kernel rip_kernel;  /* kernel variant handle; replaces cl_kernel */
 typedef struct rip_event rip_event;    /* cudaEvent_t wrapper;  replaces cl_event */
+typedef struct rip_ticket rip_ticket;  /* one job in flight in the host-buffer pipeline (rip_submit / rip_collect) */
 
 /* pixel formats of the interleaved u8 images */
 enum { RIP_FMT_GRAY8 = 1, RIP_FMT_RGB8 = 3, RIP_FMT_RGBA8 = 4, RIP_FMT_BGR8 = 5, RIP_FMT_BGRA8 = 6, RIP_FMT_NV12 = 7 };
@@ -165,13 +166,28 @@ int rip_debug_slow_path_stats(int device, int enable, uint64_t *slow_pixels);
  * sqrt + magic-number rounding for every reachable gx^2+gy^2; dot-product gray for all 2^24
  * triples) against the plain exact formulations.  mismatches must come back 0. */
 int rip_debug_selftest(int device, uint64_t *checked, uint64_t *mismatches);
+/* diagnostics: experiment switches (kernel selection for A/B runs and for the tests that compare kernels).  They are
+ * read from the environment once, at first use (RIP_DISABLE_FUSED, RIP_FUSED_SEG, RIP_FUSED_NPX, RIP_FUSED_GENERIC,
+ * RIP_BLUR_EXACT, RIP_BLUR_TILED, RIP_BLUR_STREAM); afterwards only this call changes them, so no launch path calls
+ * getenv().  `name` is the variable name with or without the RIP_ prefix.  The reference has no counterpart (its
+ * switches are file-scope globals, RealtimeImageProcessing.cpp:10-30). */
+int rip_debug_set_option(const char *name, int value);
 
 /* ---- host-buffer pipeline: what Controller::PerformCL* calls.  Shards n_frames over the devices of
  *      ctx (contiguous blocks of frames per device, no inter-device traffic), and per device runs
  *      H2D -> kernel -> D2H on cached device buffers with the copies of consecutive chunks
- *      overlapped.  Blocking: returns with h_out filled.  h_in / h_out may be pageable or pinned.
+ *      overlapped.  Every device of a context has one persistent worker thread that owns its streams,
+ *      device buffers and pinned staging buffers: no call creates a thread, and any number of host
+ *      threads may use one context concurrently.  h_in / h_out may be pinned (rip_malloc_pinned,
+ *      rip_host_register: copied by DMA directly) or pageable (std::vector, cv::Mat: staged through
+ *      the context's pinned buffers, the staging copy of one chunk overlapping the DMA of the previous).
+ *      rip_process_host is blocking: it returns with h_out filled, like the reference's PerformCL*
+ *      (RT/src/Controller.cpp:429-744: three blocking waits per call).  rip_submit / rip_collect is
+ *      the same pipeline split in two, so that the frames of a stream overlap: frame i+1 uploads while
+ *      frame i computes and frame i-1 downloads (ProgramHandler.cpp:259-329 is called once per camera
+ *      frame, RealtimeImageProcessing.cpp:355-403).  Jobs of one context complete in submission order.
  *      prof_ns (may be NULL) receives [write_start, write_end, kernel_start, kernel_end, read_start,
- *      read_end] in ns relative to the start of the call, measured with CUDA events on device 0 of
+ *      read_end] in ns relative to the start of the job, measured with CUDA events on device 0 of
  *      the context for its first chunk -- the layout of the reference's profiling_events
  *      (RT/src/Controller.cpp:66-74). ---- */
 typedef struct rip_op_desc {
@@ -185,6 +201,22 @@ typedef struct rip_op_desc {
 int rip_out_bytes_per_frame(const rip_op_desc *desc, int width, int height, size_t *bytes);
 int rip_process_host(rip_ctx *ctx, const rip_op_desc *desc, const uint8_t *h_in, uint8_t *h_out,
                      int width, int height, int n_frames, uint64_t prof_ns[6]);
+/* asynchronous form.  rip_submit copies the descriptor and the weights, queues the job on the device workers and
+ * returns at once; h_in must stay valid and h_out untouched until rip_collect(ticket) has returned.  flags:
+ * RIP_SUBMIT_BANDED = one frame split into row bands (as rip_process_host_banded), RIP_SUBMIT_PROFILE = record the
+ * events behind prof_ns.  rip_collect blocks until the job is done, frees the ticket and returns the job's status;
+ * rip_ticket_done polls.  Every ticket must be collected exactly once, before rip_ctx_destroy. */
+#define RIP_SUBMIT_BANDED 1
+#define RIP_SUBMIT_PROFILE 2
+int rip_submit(rip_ctx *ctx, const rip_op_desc *desc, const uint8_t *h_in, uint8_t *h_out, int width, int height,
+               int n_frames, int flags, rip_ticket **ticket);
+int rip_ticket_done(rip_ticket *ticket, int *done);
+int rip_collect(rip_ticket *ticket, uint64_t prof_ns[6]);
+/* page-lock / release memory the caller owns (cudaHostRegister), so that the pipeline copies it by DMA without the
+ * staging copy -- for a std::vector or cv::Mat that is reused across calls (the reference's iteration loop hands the
+ * same input_data to PerformCL* 100 times, ProgramHandler.cpp:157-216). */
+int rip_host_register(void *h_ptr, size_t bytes);
+int rip_host_unregister(void *h_ptr);
 /* The partitions the two host pipelines use (pure host arithmetic, exported so that callers and tests
  * see exactly the split that runs): part `index` of `n_parts` owns frames [first, first + count) of a
  * batch, or output rows [out_row0, out_row0 + out_rows) of a frame, for which it needs input rows

@@ -37,8 +37,9 @@ ABI_SYMBOLS = [
     "rip_malloc_device", "rip_free_device", "rip_malloc_pinned", "rip_free_pinned",
     "rip_memcpy_h2d_async", "rip_memcpy_d2h_async", "rip_memset_device_async",
     "rip_gauss_weights", "rip_gray", "rip_gauss", "rip_sobel", "rip_fused", "rip_fused_workspace_bytes",
-    "rip_launch_count", "rip_debug_slow_path_stats", "rip_debug_selftest",
+    "rip_launch_count", "rip_debug_slow_path_stats", "rip_debug_selftest", "rip_debug_set_option",
     "rip_out_bytes_per_frame", "rip_process_host", "rip_process_host_banded", "rip_shard_frames", "rip_band_rows",
+    "rip_submit", "rip_ticket_done", "rip_collect", "rip_host_register", "rip_host_unregister",
 ]
 
 
@@ -113,9 +114,15 @@ def lib() -> C.CDLL:
         "rip_launch_count": ([u64p], C.c_int),
         "rip_debug_slow_path_stats": ([C.c_int, C.c_int, u64p], C.c_int),
         "rip_debug_selftest": ([C.c_int, u64p, u64p], C.c_int),
+        "rip_debug_set_option": ([C.c_char_p, C.c_int], C.c_int),
         "rip_out_bytes_per_frame": ([C.POINTER(OpDesc), C.c_int, C.c_int, szp], C.c_int),
         "rip_process_host": ([vp, C.POINTER(OpDesc), vp, vp, C.c_int, C.c_int, C.c_int, u64p], C.c_int),
         "rip_process_host_banded": ([vp, C.POINTER(OpDesc), vp, vp, C.c_int, C.c_int, u64p], C.c_int),
+        "rip_submit": ([vp, C.POINTER(OpDesc), vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)], C.c_int),
+        "rip_ticket_done": ([vp, i32p], C.c_int),
+        "rip_collect": ([vp, u64p], C.c_int),
+        "rip_host_register": ([vp, C.c_size_t], C.c_int),
+        "rip_host_unregister": ([vp], C.c_int),
         "rip_shard_frames": ([C.c_int, C.c_int, C.c_int, i32p, i32p], C.c_int),
         "rip_band_rows": ([C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, i32p], C.c_int),
     }
@@ -185,6 +192,11 @@ def slow_path_stats(enable: bool, device: int = 0) -> int:
     v = C.c_uint64(0)
     check(lib().rip_debug_slow_path_stats(device, int(enable), C.byref(v)), "rip_debug_slow_path_stats")
     return v.value
+
+
+def set_option(name: str, value: int) -> None:
+    """Experiment switch (rip_debug_set_option): e.g. set_option("FUSED_NPX", 4)."""
+    check(lib().rip_debug_set_option(name.encode(), int(value)), "rip_debug_set_option")
 
 
 def selftest(device: int = 0) -> tuple[int, int]:
@@ -366,10 +378,7 @@ class Context:
         d.weights = _f32p(self._w)
         return d
 
-    def process(self, frames: np.ndarray, op: int, fmt: int, *, gray_out=GRAY_OUT_U8, ksize=0, weights=None,
-                out: np.ndarray | None = None, banded: bool = False, prof: bool = False):
-        """frames: (N, H, W, C) or (H, W, C) / (H, W) u8 host array (pageable or pinned); NV12: (N, H*3/2, W) or
-        (H*3/2, W), the luma plane followed by the chroma plane."""
+    def _shapes(self, frames: np.ndarray, op, fmt, gray_out, ksize, weights, out):
         a = frames
         assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"]
         cn = CHANNELS[fmt]
@@ -393,6 +402,14 @@ class Context:
         if out is None:
             out = np.empty(shape, np.uint8)
         assert out.nbytes == ob.value * n and out.flags["C_CONTIGUOUS"]
+        squeeze = frames.ndim == (2 if cn == 1 else 3)
+        return a, d, n, h, w, shape, out, squeeze
+
+    def process(self, frames: np.ndarray, op: int, fmt: int, *, gray_out=GRAY_OUT_U8, ksize=0, weights=None,
+                out: np.ndarray | None = None, banded: bool = False, prof: bool = False):
+        """frames: (N, H, W, C) or (H, W, C) / (H, W) u8 host array (pageable or pinned); NV12: (N, H*3/2, W) or
+        (H*3/2, W), the luma plane followed by the chroma plane."""
+        a, d, n, h, w, shape, out, squeeze = self._shapes(frames, op, fmt, gray_out, ksize, weights, out)
         pr = (C.c_uint64 * 6)() if prof else None
         if banded:
             assert n == 1
@@ -402,6 +419,45 @@ class Context:
             check(lib().rip_process_host(self.ptr, C.byref(d), a.ctypes.data, out.ctypes.data, w, h, n, pr),
                   "rip_process_host")
         res = out.reshape(shape)
-        if frames.ndim == (2 if cn == 1 else 3):
+        if squeeze:
             res = res[0]
         return (res, list(pr)) if prof else res
+
+    def submit(self, frames: np.ndarray, op: int, fmt: int, *, gray_out=GRAY_OUT_U8, ksize=0, weights=None,
+               out: np.ndarray | None = None, banded: bool = False, prof: bool = False) -> "Ticket":
+        """Asynchronous form of process() (rip_submit): returns at once; Ticket.collect() waits and returns the output.
+        `frames` must stay untouched until then."""
+        a, d, n, h, w, shape, out, squeeze = self._shapes(frames, op, fmt, gray_out, ksize, weights, out)
+        t = C.c_void_p()
+        flags = (1 if banded else 0) | (2 if prof else 0)
+        check(lib().rip_submit(self.ptr, C.byref(d), a.ctypes.data, out.ctypes.data, w, h, n, flags, C.byref(t)), "rip_submit")
+        return Ticket(t.value, a, out, shape, squeeze, prof)
+
+
+class Ticket:
+    """One job in flight (rip_ticket).  Keeps the input and output arrays alive until collect()."""
+
+    def __init__(self, ptr, a, out, shape, squeeze, prof):
+        self.ptr, self._in, self._out, self._shape, self._squeeze, self._prof = ptr, a, out, shape, squeeze, prof
+
+    def done(self) -> bool:
+        v = C.c_int(0)
+        check(lib().rip_ticket_done(self.ptr, C.byref(v)), "rip_ticket_done")
+        return bool(v.value)
+
+    def collect(self):
+        assert self.ptr, "ticket already collected"
+        pr = (C.c_uint64 * 6)() if self._prof else None
+        ptr, self.ptr = self.ptr, None
+        check(lib().rip_collect(ptr, pr), "rip_collect")
+        res = self._out.reshape(self._shape)
+        if self._squeeze:
+            res = res[0]
+        return (res, list(pr)) if self._prof else res
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().rip_collect(self.ptr, None)
+        except Exception:
+            pass

@@ -2,11 +2,15 @@
 // device-resident ops and the host-buffer pipeline that Controller::PerformCL* drives.
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <memory>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -42,6 +46,29 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 }
 
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static Options g_options;
+static std::once_flag g_options_once;
+static const struct { const char *name; int Options::*field; } kOptionTable[] = {
+    {"RIP_DISABLE_FUSED", &Options::disable_fused}, {"RIP_FUSED_SEG", &Options::fused_seg}, {"RIP_FUSED_NPX", &Options::fused_npx},
+    {"RIP_FUSED_GENERIC", &Options::fused_generic}, {"RIP_BLUR_EXACT", &Options::blur_exact}, {"RIP_BLUR_TILED", &Options::blur_tiled},
+    {"RIP_BLUR_STREAM", &Options::blur_stream},
+};
+
+static void load_options_from_env()
+{
+    for (const auto &o : kOptionTable)
+        if (const char *e = getenv(o.name)) {
+            const int v = atoi(e);
+            g_options.*(o.field) = (v != 0 || e[0] == '0') ? v : 1;   // "RIP_X=" or "RIP_X=yes" mean on
+        }
+}
+
+const Options &options()
+{
+    std::call_once(g_options_once, load_options_from_env);
+    return g_options;
+}
 
 int sm_count(int device)
 {
@@ -106,16 +133,21 @@ using namespace rip;
 namespace {
 constexpr int kSets = 3;  // chunk buffers in flight per device (H2D / kernel / D2H overlap)
 
+struct Part;
+
 struct BufSet {
     cudaStream_t stream = nullptr;
     void *d_in = nullptr, *d_out = nullptr, *d_ws = nullptr;
     size_t in_cap = 0, out_cap = 0, ws_cap = 0;
-};
-
-struct DevState {
-    int device = 0;
-    BufSet set[kSets];
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // pinned staging for callers that hand in pageable memory (std::vector, cv::Mat): allocated on first need
+    void *stage_in = nullptr, *stage_out = nullptr;
+    size_t stage_in_cap = 0, stage_out_cap = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // write start/end = kernel start, kernel end = read start, read end
+    // what is in flight on this set (the worker thread's bookkeeping)
+    Part *owner = nullptr;
+    uint8_t *copyout_dst = nullptr;   // pageable destination of the staged D2H (NULL: the D2H went straight to the caller)
+    size_t copyout_bytes = 0;
+    bool timed = false;
 };
 
 int ensure(void **p, size_t *cap, size_t need)
@@ -130,10 +162,70 @@ int ensure(void **p, size_t *cap, size_t need)
     *cap = want;
     return RIP_OK;
 }
+
+int ensure_pinned(void **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return RIP_OK;
+    if (*p) RIP_CUDA(cudaFreeHost(*p));
+    *p = nullptr;
+    *cap = 0;
+    const size_t want = (need + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+    RIP_CUDA(cudaHostAlloc(p, want, cudaHostAllocPortable));
+    *cap = want;
+    return RIP_OK;
+}
+
+struct DevState;
+}  // namespace
+
+// One submitted job: shared by the parts (one per device) it was cut into.
+struct rip_ticket {
+    std::mutex mu;
+    std::condition_variable cv;
+    int remaining = 0;          // parts not yet finished
+    int rc = RIP_OK;
+    std::string err;
+    double prof_ms[3] = {0, 0, 0};
+    bool want_prof = false;
+    // the job, copied at submit time (the caller's descriptor and weights need not outlive the call)
+    rip_op_desc desc;
+    std::vector<float> weights;
+    int W = 0, H = 0, cn = 0;
+    size_t in_frame_bytes = 0, out_frame_bytes = 0;
+    const uint8_t *h_in = nullptr;
+    uint8_t *h_out = nullptr;
+    bool in_pinned = false, out_pinned = false;
+    bool banded = false;
+    int n_parts = 0;
+};
+
+namespace {
+struct Part {
+    rip_ticket *t = nullptr;
+    int index = 0;              // part number within the ticket (0 carries the profile)
+    int f0 = 0, f1 = 0;         // frames [f0, f1) of the batch (frame mode)
+    int in_row0 = 0, in_rows = 0, out_row0 = 0, out_rows = 0;   // row band (banded mode)
+    int outstanding = 0;        // buffer sets still in flight for this part
+    bool issued = false;        // all chunks enqueued
+    int rc = RIP_OK;
+    std::string err;
+};
+
+struct DevState {
+    int device = 0;
+    BufSet set[kSets];
+    int next_set = 0;
+    // worker
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Part *> queue;
+    bool stop = false;
+};
 }  // namespace
 
 struct rip_ctx {
-    std::vector<DevState> devs;
+    std::vector<std::unique_ptr<DevState>> devs;
 };
 struct rip_module {
     rip_ctx *ctx;
@@ -149,6 +241,8 @@ struct rip_event {
     int device;
     cudaEvent_t ev;
 };
+
+static void worker_main(DevState *dev);
 
 // ============================================================================================
 // discovery
@@ -236,26 +330,27 @@ extern "C" int rip_ctx_create(const int *devices, int n_devices, rip_ctx **out)
     }
     rip_ctx *ctx = new (std::nothrow) rip_ctx();
     if (!ctx) return fail(RIP_ENOMEM, "rip_ctx_create: out of host memory");
-    ctx->devs.resize(devs.size());
     for (size_t i = 0; i < devs.size(); i++) {
-        DevState &d = ctx->devs[i];
+        ctx->devs.emplace_back(new DevState());
+        DevState &d = *ctx->devs.back();
         d.device = devs[i];
         DeviceGuard g(d.device);
+        if (!g.ok) {
+            rip_ctx_destroy(ctx);
+            return fail(RIP_ENODEV, "rip_ctx_create: cudaSetDevice(%d) failed", d.device);
+        }
         for (int k = 0; k < kSets; k++) {
             cudaError_t e = cudaStreamCreateWithFlags(&d.set[k].stream, cudaStreamNonBlocking);
+            for (int j = 0; j < 4 && e == cudaSuccess; j++) e = cudaEventCreate(&d.set[k].ev[j]);
             if (e != cudaSuccess) {
                 rip_ctx_destroy(ctx);
-                return cuda_fail(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
-            }
-        }
-        for (int k = 0; k < 4; k++) {
-            cudaError_t e = cudaEventCreate(&d.ev[k]);
-            if (e != cudaSuccess) {
-                rip_ctx_destroy(ctx);
-                return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
+                return cuda_fail(e, "cudaStreamCreateWithFlags / cudaEventCreate", __FILE__, __LINE__);
             }
         }
     }
+    // one persistent worker thread per device: it owns the device's buffer sets and streams, so no call ever
+    // creates a thread and two host threads may use the same context concurrently
+    for (auto &d : ctx->devs) d->worker = std::thread(worker_main, d.get());
     *out = ctx;
     return RIP_OK;
 }
@@ -263,7 +358,16 @@ extern "C" int rip_ctx_create(const int *devices, int n_devices, rip_ctx **out)
 extern "C" int rip_ctx_destroy(rip_ctx *ctx)
 {
     if (!ctx) return RIP_OK;
-    for (DevState &d : ctx->devs) {
+    for (auto &dp : ctx->devs) {
+        DevState &d = *dp;
+        if (d.worker.joinable()) {
+            {
+                std::lock_guard<std::mutex> lk(d.mu);
+                d.stop = true;   // (the worker drains its queue before it leaves)
+            }
+            d.cv.notify_all();
+            d.worker.join();
+        }
         DeviceGuard g(d.device);
         for (int k = 0; k < kSets; k++) {
             BufSet &b = d.set[k];
@@ -274,9 +378,11 @@ extern "C" int rip_ctx_destroy(rip_ctx *ctx)
             if (b.d_in) cudaFree(b.d_in);
             if (b.d_out) cudaFree(b.d_out);
             if (b.d_ws) cudaFree(b.d_ws);
+            if (b.stage_in) cudaFreeHost(b.stage_in);
+            if (b.stage_out) cudaFreeHost(b.stage_out);
+            for (int j = 0; j < 4; j++)
+                if (b.ev[j]) cudaEventDestroy(b.ev[j]);
         }
-        for (int k = 0; k < 4; k++)
-            if (d.ev[k]) cudaEventDestroy(d.ev[k]);
     }
     delete ctx;
     return RIP_OK;
@@ -293,7 +399,7 @@ extern "C" int rip_ctx_device(const rip_ctx *ctx, int index, int *device)
 {
     if (!ctx || !device) return fail(RIP_EINVAL, "rip_ctx_device: NULL");
     if (index < 0 || index >= (int)ctx->devs.size()) return fail(RIP_EINVAL, "rip_ctx_device: index %d out of range", index);
-    *device = ctx->devs[index].device;
+    *device = ctx->devs[index]->device;
     return RIP_OK;
 }
 
@@ -656,6 +762,18 @@ extern "C" int rip_debug_slow_path_stats(int device, int enable, uint64_t *slow_
     return RIP_OK;
 }
 
+extern "C" int rip_debug_set_option(const char *name, int value)
+{
+    if (!name) return fail(RIP_EINVAL, "rip_debug_set_option: NULL");
+    options();   // (the environment is read first, so that a later first use cannot overwrite this call)
+    for (const auto &o : kOptionTable)
+        if (!strcmp(name, o.name) || !strcmp(name, o.name + 4)) {
+            g_options.*(o.field) = value;
+            return RIP_OK;
+        }
+    return fail(RIP_EINVAL, "rip_debug_set_option: unknown option '%s'", name);
+}
+
 extern "C" int rip_debug_selftest(int device, uint64_t *checked, uint64_t *mismatches)
 {
     if (!checked || !mismatches) return fail(RIP_EINVAL, "rip_debug_selftest: NULL");
@@ -692,35 +810,6 @@ bool fused_single_kernel(int W, int H, int fmt, int ksize, const float *weights,
            fused_plan_weights(weights, g3, &thr);
 }
 
-struct Job {
-    const rip_op_desc *desc;
-    int W, H;
-    int cn;
-    size_t in_frame_bytes, out_frame_bytes;
-};
-
-// enqueue one operation on device-resident frames (whole frames)
-int enqueue_op(const Job &job, int device, const BufSet &b, int n_frames)
-{
-    const rip_op_desc &d = *job.desc;
-    cudaStream_t s = b.stream;
-    const uint8_t *in = (const uint8_t *)b.d_in;
-    uint8_t *out = (uint8_t *)b.d_out;
-    switch (d.op) {
-    case RIP_OP_GRAY:
-        return rip_gray(device, s, in, out, job.W, job.H, n_frames, d.in_format, d.gray_out);
-    case RIP_OP_EDGE:
-        return rip_sobel(device, s, in, out, job.W, job.H, n_frames, d.in_format);
-    case RIP_OP_GAUSSIAN:
-        return rip_gauss(device, s, in, out, job.W, job.H, n_frames, job.cn, d.ksize, d.weights);
-    case RIP_OP_FUSED:
-        return rip_fused(device, s, in, out, job.W, job.H, n_frames, d.in_format, d.ksize, d.weights, 0, job.H, 0, job.H,
-                         b.d_ws, b.ws_cap);
-    default:
-        return fail(RIP_EINVAL, "unknown op %d", d.op);
-    }
-}
-
 int validate_desc(const rip_op_desc *desc, int *cn_out)
 {
     if (!desc) return fail(RIP_EINVAL, "rip_process_host: NULL descriptor");
@@ -746,66 +835,194 @@ int validate_desc(const rip_op_desc *desc, int *cn_out)
     return RIP_OK;
 }
 
-// Process frames [f0, f1) of the batch on one device: chunks of frames cycle through kSets buffer
-// sets, each with its own stream, so the H2D of chunk i+1 and the D2H of chunk i-1 overlap the
-// kernel of chunk i.  If prof != NULL the first chunk is bracketed by events.
-int run_device(DevState &dev, const Job &job, const uint8_t *h_in, uint8_t *h_out, int f0, int f1, double *prof_ms, char *err,
-               size_t err_len)
+// gray -> Sobel on one row band of a single frame (the band's input rows are device-resident at d_in)
+int rip_sobel_rows(int device, cudaStream_t s, const uint8_t *d_in, uint8_t *d_out, int W, int H, int fmt, int in_row0, int in_rows,
+                   int out_row0, int out_rows)
 {
-    int rc = RIP_OK;
-    {
-        DeviceGuard g(dev.device);
-        const int n = f1 - f0;
-        // ~48 MiB of input per chunk keeps three chunks in flight without hoarding HBM
-        int chunk = (int)((size_t)(48u << 20) / job.in_frame_bytes);
-        if (chunk < 1) chunk = 1;
-        if (chunk > n) chunk = n;
-        int k = 0;
-        for (int c0 = 0; c0 < n && rc == RIP_OK; c0 += chunk, k++) {
-            const int cf = (n - c0 < chunk) ? n - c0 : chunk;
-            BufSet &b = dev.set[k % kSets];
-            if (k >= kSets) rc = (int)cudaStreamSynchronize(b.stream);  // previous user of this set is done
-            if (rc) { rc = cuda_fail((cudaError_t)rc, "cudaStreamSynchronize", __FILE__, __LINE__); break; }
-            if ((rc = ensure(&b.d_in, &b.in_cap, job.in_frame_bytes * cf))) break;
-            if ((rc = ensure(&b.d_out, &b.out_cap, job.out_frame_bytes * cf))) break;
-            if (job.desc->op == RIP_OP_FUSED &&
-                !fused_single_kernel(job.W, job.H, job.desc->in_format, job.desc->ksize, job.desc->weights, b.d_in, b.d_out)) {
-                size_t ws_need = 0;  // staged path only
-                rip_fused_workspace_bytes(job.W, job.H, cf, job.desc->ksize, &ws_need);
-                if ((rc = ensure(&b.d_ws, &b.ws_cap, ws_need))) break;
-            }
-            const bool timed = prof_ms && k == 0;
-            const uint8_t *src = h_in + (size_t)(f0 + c0) * job.in_frame_bytes;
-            uint8_t *dst = h_out + (size_t)(f0 + c0) * job.out_frame_bytes;
-            if (timed) cudaEventRecord(dev.ev[0], b.stream);
-            if ((rc = (int)cudaMemcpyAsync(b.d_in, src, job.in_frame_bytes * cf, cudaMemcpyHostToDevice, b.stream))) {
-                rc = cuda_fail((cudaError_t)rc, "cudaMemcpyAsync(H2D)", __FILE__, __LINE__);
-                break;
-            }
-            if (timed) cudaEventRecord(dev.ev[1], b.stream);
-            if ((rc = enqueue_op(job, dev.device, b, cf))) break;
-            if (timed) cudaEventRecord(dev.ev[2], b.stream);
-            if ((rc = (int)cudaMemcpyAsync(dst, b.d_out, job.out_frame_bytes * cf, cudaMemcpyDeviceToHost, b.stream))) {
-                rc = cuda_fail((cudaError_t)rc, "cudaMemcpyAsync(D2H)", __FILE__, __LINE__);
-                break;
-            }
-            if (timed) cudaEventRecord(dev.ev[3], b.stream);
-        }
-        for (int i = 0; i < kSets; i++) {
-            cudaError_t e = cudaStreamSynchronize(dev.set[i].stream);
-            if (e != cudaSuccess && rc == RIP_OK) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
-        }
-        if (rc == RIP_OK && prof_ms) {
-            float a = 0, bms = 0, c = 0;
-            cudaEventElapsedTime(&a, dev.ev[0], dev.ev[1]);
-            cudaEventElapsedTime(&bms, dev.ev[1], dev.ev[2]);
-            cudaEventElapsedTime(&c, dev.ev[2], dev.ev[3]);
-            prof_ms[0] = a; prof_ms[1] = bms; prof_ms[2] = c;
-        }
-    }
-    if (rc != RIP_OK && err) snprintf(err, err_len, "%s", rip_last_error_string());
-    return rc;
+    DeviceGuard g(device);
+    if (fused_supported(W, H, fmt, 0, d_in, d_out))
+        return launch_fused(s, d_in, d_out, W, H, 1, fmt, false, nullptr, in_row0, in_rows, out_row0, out_rows, device);
+    return launch_sobel(s, d_in, d_out, W, H, 1, fmt == RIP_FMT_NV12 ? RIP_FMT_GRAY8 : fmt, in_row0, in_rows, out_row0, out_rows);
 }
+
+// ---- the worker side ----------------------------------------------------------------------------------------
+
+// enqueue one operation on device-resident data: `n_frames` whole frames, or one row band of a single frame
+int enqueue_op(const rip_ticket &t, int device, const BufSet &b, int n_frames, const Part *band)
+{
+    const rip_op_desc &d = t.desc;
+    cudaStream_t s = b.stream;
+    const uint8_t *in = (const uint8_t *)b.d_in;
+    uint8_t *out = (uint8_t *)b.d_out;
+    if (band) {
+        if (d.op == RIP_OP_FUSED)
+            return rip_fused(device, s, in, out, t.W, t.H, 1, d.in_format, d.ksize, d.weights, band->in_row0, band->in_rows,
+                             band->out_row0, band->out_rows, b.d_ws, b.ws_cap);
+        return rip_sobel_rows(device, s, in, out, t.W, t.H, d.in_format, band->in_row0, band->in_rows, band->out_row0, band->out_rows);
+    }
+    switch (d.op) {
+    case RIP_OP_GRAY:
+        return rip_gray(device, s, in, out, t.W, t.H, n_frames, d.in_format, d.gray_out);
+    case RIP_OP_EDGE:
+        return rip_sobel(device, s, in, out, t.W, t.H, n_frames, d.in_format);
+    case RIP_OP_GAUSSIAN:
+        return rip_gauss(device, s, in, out, t.W, t.H, n_frames, t.cn, d.ksize, d.weights);
+    case RIP_OP_FUSED:
+        return rip_fused(device, s, in, out, t.W, t.H, n_frames, d.in_format, d.ksize, d.weights, 0, t.H, 0, t.H, b.d_ws, b.ws_cap);
+    default:
+        return fail(RIP_EINVAL, "unknown op %d", d.op);
+    }
+}
+
+void finish_part(Part *p)
+{
+    rip_ticket *t = p->t;
+    bool last;
+    {
+        std::lock_guard<std::mutex> lk(t->mu);
+        if (p->rc != RIP_OK && t->rc == RIP_OK) {
+            t->rc = p->rc;
+            t->err = p->err;
+        }
+        last = --t->remaining == 0;
+        if (last) t->cv.notify_all();   // (under the lock: rip_collect may delete the ticket as soon as it sees 0)
+    }
+    delete p;
+}
+
+// Wait until buffer set `b` is free again: its stream has drained, a staged result has been copied out to the
+// caller's pageable buffer, the profile (if this was the timed chunk) is read, and its part is told.
+void retire_set(BufSet &b)
+{
+    if (!b.owner) return;
+    Part *p = b.owner;
+    cudaError_t e = cudaStreamSynchronize(b.stream);
+    if (e != cudaSuccess && p->rc == RIP_OK) {
+        p->rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+        p->err = rip_last_error_string();
+    }
+    if (p->rc == RIP_OK && b.copyout_dst) memcpy(b.copyout_dst, b.stage_out, b.copyout_bytes);
+    if (p->rc == RIP_OK && b.timed) {
+        float w = 0, k = 0, r = 0;
+        cudaEventElapsedTime(&w, b.ev[0], b.ev[1]);
+        cudaEventElapsedTime(&k, b.ev[1], b.ev[2]);
+        cudaEventElapsedTime(&r, b.ev[2], b.ev[3]);
+        std::lock_guard<std::mutex> lk(p->t->mu);
+        p->t->prof_ms[0] = w; p->t->prof_ms[1] = k; p->t->prof_ms[2] = r;
+    }
+    b.owner = nullptr;
+    b.copyout_dst = nullptr;
+    b.timed = false;
+    if (--p->outstanding == 0 && p->issued) finish_part(p);
+}
+
+// Enqueue every chunk of one part.  Chunks cycle through the kSets buffer sets, each with its own stream, so the H2D
+// of chunk i+1 and the D2H of chunk i-1 overlap the kernel of chunk i -- and, because nothing here waits for the
+// part's own completion, the first chunks of the NEXT part in the queue overlap the tail of this one.
+void issue_part(DevState &dev, Part *p)
+{
+    rip_ticket &t = *p->t;
+    const bool band = t.banded;
+    const int n = band ? 1 : p->f1 - p->f0;
+    // ~48 MiB of input per chunk keeps three chunks in flight without hoarding HBM
+    int chunk = band ? 1 : (int)((size_t)(48u << 20) / (t.in_frame_bytes ? t.in_frame_bytes : 1));
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    const size_t row_in = (size_t)t.W * t.cn;
+    int rc = RIP_OK;
+    p->outstanding = 1;   // (guards against finishing while still issuing)
+    for (int c0 = 0; c0 < n && rc == RIP_OK; c0 += chunk) {
+        const int cf = (n - c0 < chunk) ? n - c0 : chunk;
+        BufSet &b = dev.set[dev.next_set];
+        dev.next_set = (dev.next_set + 1) % kSets;
+        retire_set(b);   // previous user of this set (of this part or of an earlier one) is done
+        const size_t in_bytes = band ? row_in * p->in_rows : t.in_frame_bytes * cf;
+        const size_t out_bytes = band ? (size_t)t.W * p->out_rows : t.out_frame_bytes * cf;
+        const uint8_t *src = band ? t.h_in + row_in * p->in_row0 : t.h_in + (size_t)(p->f0 + c0) * t.in_frame_bytes;
+        uint8_t *dst = band ? t.h_out + (size_t)t.W * p->out_row0 : t.h_out + (size_t)(p->f0 + c0) * t.out_frame_bytes;
+        if ((rc = ensure(&b.d_in, &b.in_cap, in_bytes))) break;
+        if ((rc = ensure(&b.d_out, &b.out_cap, out_bytes))) break;
+        if (t.desc.op == RIP_OP_FUSED &&
+            !fused_single_kernel(t.W, t.H, t.desc.in_format, t.desc.ksize, t.desc.weights, b.d_in, b.d_out)) {
+            size_t ws_need = 0;  // staged path only
+            rip_fused_workspace_bytes(t.W, band ? p->in_rows : t.H, cf, t.desc.ksize, &ws_need);
+            if ((rc = ensure(&b.d_ws, &b.ws_cap, ws_need))) break;
+        }
+        if (!t.in_pinned) {   // pageable source: stage through pinned memory (the copy overlaps the DMA of the previous chunk)
+            if ((rc = ensure_pinned(&b.stage_in, &b.stage_in_cap, in_bytes))) break;
+            memcpy(b.stage_in, src, in_bytes);
+            src = (const uint8_t *)b.stage_in;
+        }
+        uint8_t *d2h_dst = dst;
+        if (!t.out_pinned) {
+            if ((rc = ensure_pinned(&b.stage_out, &b.stage_out_cap, out_bytes))) break;
+            d2h_dst = (uint8_t *)b.stage_out;
+        }
+        const bool timed = t.want_prof && p->index == 0 && c0 == 0;
+        cudaError_t e = cudaSuccess;
+        if (timed) cudaEventRecord(b.ev[0], b.stream);
+        if ((e = cudaMemcpyAsync(b.d_in, src, in_bytes, cudaMemcpyHostToDevice, b.stream)) != cudaSuccess) {
+            rc = cuda_fail(e, "cudaMemcpyAsync(H2D)", __FILE__, __LINE__);
+            break;
+        }
+        if (timed) cudaEventRecord(b.ev[1], b.stream);
+        if ((rc = enqueue_op(t, dev.device, b, cf, band ? p : nullptr))) break;
+        if (timed) cudaEventRecord(b.ev[2], b.stream);
+        if ((e = cudaMemcpyAsync(d2h_dst, b.d_out, out_bytes, cudaMemcpyDeviceToHost, b.stream)) != cudaSuccess) {
+            rc = cuda_fail(e, "cudaMemcpyAsync(D2H)", __FILE__, __LINE__);
+            break;
+        }
+        if (timed) cudaEventRecord(b.ev[3], b.stream);
+        b.owner = p;
+        b.copyout_dst = t.out_pinned ? nullptr : dst;
+        b.copyout_bytes = out_bytes;
+        b.timed = timed;
+        p->outstanding++;
+    }
+    if (rc != RIP_OK && p->rc == RIP_OK) {
+        p->rc = rc;
+        p->err = rip_last_error_string();
+    }
+    p->issued = true;
+    if (--p->outstanding == 0) finish_part(p);
+}
+
+}  // namespace
+
+static void worker_main(DevState *dev)
+{
+    const bool dev_ok = cudaSetDevice(dev->device) == cudaSuccess;
+    for (;;) {
+        Part *p = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(dev->mu);
+            if (dev->queue.empty() && !dev->stop) {
+                // nothing queued: retire what is in flight (oldest first), then sleep
+                lk.unlock();
+                for (int k = 0; k < kSets; k++) retire_set(dev->set[(dev->next_set + k) % kSets]);
+                lk.lock();
+                dev->cv.wait(lk, [&] { return dev->stop || !dev->queue.empty(); });
+            }
+            if (dev->queue.empty()) {
+                if (dev->stop) break;
+                continue;
+            }
+            p = dev->queue.front();
+            dev->queue.pop_front();
+        }
+        if (!dev_ok) {
+            p->rc = fail(RIP_ENODEV, "cudaSetDevice(%d) failed in the device worker", dev->device);
+            p->err = rip_last_error_string();
+            p->issued = true;
+            finish_part(p);
+            continue;
+        }
+        issue_part(*dev, p);
+    }
+    for (int k = 0; k < kSets; k++) retire_set(dev->set[(dev->next_set + k) % kSets]);
+}
+
+namespace {
 
 void fill_prof(uint64_t prof_ns[6], const double ms[3])
 {
@@ -817,6 +1034,18 @@ void fill_prof(uint64_t prof_ns[6], const double ms[3])
     prof_ns[3] = (uint64_t)llround(w + k);
     prof_ns[4] = prof_ns[3];
     prof_ns[5] = (uint64_t)llround(w + k + r);
+}
+
+// pinned (cudaHostAlloc / cudaHostRegister) or managed memory can be handed to cudaMemcpyAsync directly; anything
+// else is pageable and goes through the context's pinned staging buffers
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
 }  // namespace
@@ -842,125 +1071,122 @@ extern "C" int rip_band_rows(int height, int n_parts, int index, int halo, int *
     return RIP_OK;
 }
 
+extern "C" int rip_submit(rip_ctx *ctx, const rip_op_desc *desc, const uint8_t *h_in, uint8_t *h_out, int width, int height,
+                          int n_frames, int flags, rip_ticket **ticket)
+{
+    if (!ticket) return fail(RIP_EINVAL, "rip_submit: NULL ticket pointer");
+    *ticket = nullptr;
+    if (!ctx || ctx->devs.empty()) return fail(RIP_EINVAL, "rip_submit: NULL context");
+    if (!h_in || !h_out) return fail(RIP_EINVAL, "rip_submit: NULL host buffer");
+    if (width <= 0 || height <= 0 || n_frames <= 0)
+        return fail(RIP_EINVAL, "rip_submit: width, height and n_frames must be positive (got %d x %d x %d)", width, height, n_frames);
+    int cn = 0;
+    if (int rc = validate_desc(desc, &cn)) return rc;
+    if (desc->in_format == RIP_FMT_NV12 && (height & 1)) return fail(RIP_EINVAL, "NV12 frames need an even height (got %d)", height);
+    const bool banded = (flags & RIP_SUBMIT_BANDED) != 0;
+    if (banded) {
+        if (n_frames != 1) return fail(RIP_EINVAL, "row-band mode takes one frame per call (got %d)", n_frames);
+        if (desc->op != RIP_OP_FUSED && desc->op != RIP_OP_EDGE) return fail(RIP_EUNSUPPORTED, "row-band mode supports FUSED and EDGE only");
+    }
+    std::unique_ptr<rip_ticket> t(new (std::nothrow) rip_ticket());
+    if (!t) return fail(RIP_ENOMEM, "rip_submit: out of host memory");
+    t->desc = *desc;
+    if (desc->weights && (desc->op == RIP_OP_GAUSSIAN || desc->op == RIP_OP_FUSED)) {
+        if (desc->ksize < 1 || desc->ksize > RIP_MAX_KSIZE || !(desc->ksize & 1))
+            return fail(RIP_EINVAL, "kernel size must be odd and in [1,%d] (got %d)", RIP_MAX_KSIZE, desc->ksize);
+        t->weights.assign(desc->weights, desc->weights + desc->ksize * desc->ksize);
+        t->desc.weights = t->weights.data();
+    }
+    t->W = width; t->H = height; t->cn = cn;
+    t->in_frame_bytes = frame_bytes_of(desc->in_format, width, height);
+    if (int rc = rip_out_bytes_per_frame(desc, width, height, &t->out_frame_bytes)) return rc;
+    t->h_in = h_in; t->h_out = h_out;
+    t->in_pinned = is_pinned(h_in);
+    t->out_pinned = is_pinned(h_out);
+    t->banded = banded;
+    t->want_prof = (flags & RIP_SUBMIT_PROFILE) != 0;
+    const int nd = (int)ctx->devs.size();
+    const int units = banded ? height : n_frames;
+    const int used = units < nd ? units : nd;
+    const int halo = desc->op == RIP_OP_FUSED ? desc->ksize / 2 + 1 : 1;
+    t->n_parts = used;
+    t->remaining = used;
+    std::vector<Part *> parts;
+    for (int i = 0; i < used; i++) {
+        Part *p = new Part();
+        p->t = t.get();
+        p->index = i;
+        if (banded) rip_band_rows(height, used, i, halo, &p->in_row0, &p->in_rows, &p->out_row0, &p->out_rows);
+        else {
+            int fc = 0;
+            rip_shard_frames(n_frames, used, i, &p->f0, &fc);
+            p->f1 = p->f0 + fc;
+        }
+        parts.push_back(p);
+    }
+    rip_ticket *raw = t.release();
+    for (int i = 0; i < used; i++) {
+        DevState &d = *ctx->devs[i];
+        {
+            std::lock_guard<std::mutex> lk(d.mu);
+            d.queue.push_back(parts[i]);
+        }
+        d.cv.notify_one();
+    }
+    *ticket = raw;
+    return RIP_OK;
+}
+
+extern "C" int rip_ticket_done(rip_ticket *ticket, int *done)
+{
+    if (!ticket || !done) return fail(RIP_EINVAL, "rip_ticket_done: NULL");
+    std::lock_guard<std::mutex> lk(ticket->mu);
+    *done = ticket->remaining == 0;
+    return RIP_OK;
+}
+
+extern "C" int rip_collect(rip_ticket *ticket, uint64_t prof_ns[6])
+{
+    if (!ticket) return fail(RIP_EINVAL, "rip_collect: NULL ticket");
+    int rc;
+    {
+        std::unique_lock<std::mutex> lk(ticket->mu);
+        ticket->cv.wait(lk, [&] { return ticket->remaining == 0; });
+        rc = ticket->rc;
+        if (rc != RIP_OK) fail(rc, "%s", ticket->err.c_str());
+        else if (prof_ns) fill_prof(prof_ns, ticket->prof_ms);
+    }
+    delete ticket;
+    return rc;
+}
+
 extern "C" int rip_process_host(rip_ctx *ctx, const rip_op_desc *desc, const uint8_t *h_in, uint8_t *h_out, int width,
                                 int height, int n_frames, uint64_t prof_ns[6])
 {
-    if (!ctx) return fail(RIP_EINVAL, "rip_process_host: NULL context");
-    if (!h_in || !h_out) return fail(RIP_EINVAL, "rip_process_host: NULL host buffer");
-    if (width <= 0 || height <= 0 || n_frames <= 0)
-        return fail(RIP_EINVAL, "rip_process_host: width, height and n_frames must be positive (got %d x %d x %d)", width, height, n_frames);
-    Job job;
-    job.desc = desc;
-    job.W = width;
-    job.H = height;
-    if (int rc = validate_desc(desc, &job.cn)) return rc;
-    if (desc->in_format == RIP_FMT_NV12 && (height & 1)) return fail(RIP_EINVAL, "NV12 frames need an even height (got %d)", height);
-    job.in_frame_bytes = frame_bytes_of(desc->in_format, width, height);
-    if (int rc = rip_out_bytes_per_frame(desc, width, height, &job.out_frame_bytes)) return rc;
-
-    const int nd = (int)ctx->devs.size();
-    const int used = n_frames < nd ? n_frames : nd;
-    double prof_ms[3] = {0, 0, 0};
-    if (used == 1) {
-        int rc = run_device(ctx->devs[0], job, h_in, h_out, 0, n_frames, prof_ns ? prof_ms : nullptr, nullptr, 0);
-        if (rc == RIP_OK && prof_ns) fill_prof(prof_ns, prof_ms);
-        return rc;
-    }
-    // contiguous blocks of frames per device; one host thread per device, no inter-device traffic
-    std::vector<std::thread> th;
-    std::vector<int> rcs(used, RIP_OK);
-    std::vector<std::string> errs(used, std::string(512, '\0'));
-    for (int i = 0; i < used; i++) {
-        int f0 = 0, fc = 0;
-        rip_shard_frames(n_frames, used, i, &f0, &fc);
-        const int f1 = f0 + fc;
-        th.emplace_back([&, i, f0, f1]() {
-            rcs[i] = run_device(ctx->devs[i], job, h_in, h_out, f0, f1, (i == 0 && prof_ns) ? prof_ms : nullptr, &errs[i][0], errs[i].size());
-        });
-    }
-    for (auto &t : th) t.join();
-    for (int i = 0; i < used; i++)
-        if (rcs[i] != RIP_OK) return fail(rcs[i], "device %d: %s", ctx->devs[i].device, errs[i].c_str());
-    if (prof_ns) fill_prof(prof_ns, prof_ms);
-    return RIP_OK;
+    rip_ticket *t = nullptr;
+    if (int rc = rip_submit(ctx, desc, h_in, h_out, width, height, n_frames, prof_ns ? RIP_SUBMIT_PROFILE : 0, &t)) return rc;
+    return rip_collect(t, prof_ns);
 }
 
 extern "C" int rip_process_host_banded(rip_ctx *ctx, const rip_op_desc *desc, const uint8_t *h_in, uint8_t *h_out,
                                        int width, int height, uint64_t prof_ns[6])
 {
-    if (!ctx) return fail(RIP_EINVAL, "rip_process_host_banded: NULL context");
-    if (!h_in || !h_out) return fail(RIP_EINVAL, "rip_process_host_banded: NULL host buffer");
-    if (width <= 0 || height <= 0) return fail(RIP_EINVAL, "rip_process_host_banded: bad shape %d x %d", width, height);
-    int cn = 0;
-    if (int rc = validate_desc(desc, &cn)) return rc;
-    if (desc->op != RIP_OP_FUSED && desc->op != RIP_OP_EDGE)
-        return fail(RIP_EUNSUPPORTED, "row-band mode supports FUSED and EDGE only");
-    const int halo = desc->op == RIP_OP_FUSED ? desc->ksize / 2 + 1 : 1;
-    int nd = (int)ctx->devs.size();
-    if (nd > height) nd = height;
-    std::vector<std::thread> th;
-    std::vector<int> rcs(nd, RIP_OK);
-    std::vector<std::string> errs(nd, std::string(512, '\0'));
-    double prof_ms[3] = {0, 0, 0};
-    const size_t row_in = (size_t)width * cn;
-    for (int i = 0; i < nd; i++) {
-        th.emplace_back([&, i]() {
-            DevState &dev = ctx->devs[i];
-            int rc = RIP_OK;
-            {
-                DeviceGuard g(dev.device);
-                int o0 = 0, on = 0, i0 = 0, in = 0;
-                rip_band_rows(height, nd, i, halo, &i0, &in, &o0, &on);
-                const int o1 = o0 + on, i1 = i0 + in;
-                BufSet &b = dev.set[0];
-                do {
-                    if ((rc = ensure(&b.d_in, &b.in_cap, row_in * (i1 - i0)))) break;
-                    if ((rc = ensure(&b.d_out, &b.out_cap, (size_t)width * (o1 - o0)))) break;
-                    if (desc->op == RIP_OP_FUSED &&
-                        !fused_single_kernel(width, height, desc->in_format, desc->ksize, desc->weights, b.d_in, b.d_out)) {
-                        size_t ws_need = 0;  // staged path only
-                        rip_fused_workspace_bytes(width, i1 - i0, 1, desc->ksize, &ws_need);
-                        if ((rc = ensure(&b.d_ws, &b.ws_cap, ws_need))) break;
-                    }
-                    const bool timed = prof_ns && i == 0;
-                    if (timed) cudaEventRecord(dev.ev[0], b.stream);
-                    cudaError_t e = cudaMemcpyAsync(b.d_in, h_in + row_in * i0, row_in * (i1 - i0), cudaMemcpyHostToDevice, b.stream);
-                    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(H2D)", __FILE__, __LINE__); break; }
-                    if (timed) cudaEventRecord(dev.ev[1], b.stream);
-                    if (desc->op == RIP_OP_FUSED) {
-                        rc = rip_fused(dev.device, b.stream, (const uint8_t *)b.d_in, (uint8_t *)b.d_out, width, height, 1,
-                                       desc->in_format, desc->ksize, desc->weights, i0, i1 - i0, o0, o1 - o0, b.d_ws, b.ws_cap);
-                    } else if (fused_supported(width, height, desc->in_format, 0, (const uint8_t *)b.d_in, (uint8_t *)b.d_out)) {
-                        rc = launch_fused(b.stream, (const uint8_t *)b.d_in, (uint8_t *)b.d_out, width, height, 1, desc->in_format, false,
-                                          nullptr, i0, i1 - i0, o0, o1 - o0, dev.device);
-                    } else {
-                        rc = launch_sobel(b.stream, (const uint8_t *)b.d_in, (uint8_t *)b.d_out, width, height, 1,
-                                          desc->in_format == RIP_FMT_NV12 ? RIP_FMT_GRAY8 : desc->in_format, i0,
-                                          i1 - i0, o0, o1 - o0);
-                    }
-                    if (rc) break;
-                    if (timed) cudaEventRecord(dev.ev[2], b.stream);
-                    e = cudaMemcpyAsync(h_out + (size_t)width * o0, b.d_out, (size_t)width * (o1 - o0), cudaMemcpyDeviceToHost, b.stream);
-                    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(D2H)", __FILE__, __LINE__); break; }
-                    if (timed) cudaEventRecord(dev.ev[3], b.stream);
-                    e = cudaStreamSynchronize(b.stream);
-                    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__); break; }
-                    if (timed) {
-                        float a = 0, k = 0, c = 0;
-                        cudaEventElapsedTime(&a, dev.ev[0], dev.ev[1]);
-                        cudaEventElapsedTime(&k, dev.ev[1], dev.ev[2]);
-                        cudaEventElapsedTime(&c, dev.ev[2], dev.ev[3]);
-                        prof_ms[0] = a; prof_ms[1] = k; prof_ms[2] = c;
-                    }
-                } while (0);
-            }
-            if (rc != RIP_OK) snprintf(&errs[i][0], errs[i].size(), "%s", rip_last_error_string());
-            rcs[i] = rc;
-        });
-    }
-    for (auto &t : th) t.join();
-    for (int i = 0; i < nd; i++)
-        if (rcs[i] != RIP_OK) return fail(rcs[i], "device %d: %s", ctx->devs[i].device, errs[i].c_str());
-    if (prof_ns) fill_prof(prof_ns, prof_ms);
+    rip_ticket *t = nullptr;
+    if (int rc = rip_submit(ctx, desc, h_in, h_out, width, height, 1, RIP_SUBMIT_BANDED | (prof_ns ? RIP_SUBMIT_PROFILE : 0), &t)) return rc;
+    return rip_collect(t, prof_ns);
+}
+
+extern "C" int rip_host_register(void *h_ptr, size_t bytes)
+{
+    if (!h_ptr || !bytes) return fail(RIP_EINVAL, "rip_host_register: NULL / empty range");
+    if (int rc = check_device(0)) return rc;
+    RIP_CUDA(cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable));
+    return RIP_OK;
+}
+
+extern "C" int rip_host_unregister(void *h_ptr)
+{
+    if (!h_ptr) return RIP_OK;
+    RIP_CUDA(cudaHostUnregister(h_ptr));
     return RIP_OK;
 }

@@ -232,7 +232,7 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
                     const Weights &wts, int src_row0, int src_rows, int out_row0, int out_rows)
 {
     if ((cn != 1 && cn != 4) || ksize < 3) return RIP_EUNSUPPORTED;
-    if (getenv("RIP_BLUR_EXACT")) return RIP_EUNSUPPORTED;   // (tests compare the two kernels)
+    if (options().blur_exact) return RIP_EUNSUPPORTED;   // (tests compare the two kernels)
     if (cn == 4 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u)) return RIP_EUNSUPPORTED;
     SepParams p;
     memset(&p, 0, sizeof(p));
@@ -250,7 +250,7 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
     // 5x5 RGBA: the streaming kernel for large inputs (1.4x the tiled kernel on 16 1080p frames), the tiled one for
     // small ones, where a block per 32x32 tile exposes more parallelism (one 683x1023 frame: 25 us against 31 us)
     const bool big = (long long)n_frames * out_rows * W >= (2LL << 20);
-    if (cn == 4 && ksize == 5 && !getenv("RIP_BLUR_TILED") && (big || getenv("RIP_BLUR_STREAM"))) {
+    if (cn == 4 && ksize == 5 && !options().blur_tiled && (big || options().blur_stream)) {
         // the streaming kernel: bands of 60 columns per warp, segments of rows sized so that the grid fills the GPU
         // (4 warm-up rows per segment)
         StreamGeo sg;

@@ -44,6 +44,20 @@ struct DeviceGuard {
 };
 
 int sm_count(int device);
+constexpr int kMaxGridZ = 65535;   // frames per launch of the kernels that index frames with blockIdx.z
+
+// Debug / experiment switches.  Read from the environment ONCE (first use), then only changed through
+// rip_debug_set_option(): no getenv() on any launch path.
+struct Options {
+    int disable_fused = 0;   // RIP_DISABLE_FUSED: never take the single-kernel fused path
+    int fused_seg = 0;       // RIP_FUSED_SEG:     rows per segment of the fused kernel (0 = automatic)
+    int fused_npx = 0;       // RIP_FUSED_NPX:     4 = force the 4-pixel-per-lane kernel (0 / 8 = automatic)
+    int fused_generic = 0;   // RIP_FUSED_GENERIC: always run the any-shape tile kernel
+    int blur_exact = 0;      // RIP_BLUR_EXACT:    always run the reference-order blur kernel
+    int blur_tiled = 0;      // RIP_BLUR_TILED:    never run the streaming blur kernels
+    int blur_stream = 0;     // RIP_BLUR_STREAM:   run the streaming blur kernels on small inputs too
+};
+const Options &options();
 
 // KxK weights passed by value: lives in the kernel-parameter constant bank, so every tap is a
 // uniform constant-cache read and concurrent streams can use different kernels safely.

@@ -94,7 +94,7 @@ bool fused_supported(int W, int H, int fmt, int ksize, const uint8_t *d_in, cons
     if (fmt == RIP_FMT_NV12 && (H & 1)) return false;
     const uintptr_t in_align = cn == 4 ? 15u : 3u;
     if ((reinterpret_cast<uintptr_t>(d_in) & in_align) || (reinterpret_cast<uintptr_t>(d_out) & 3u)) return false;
-    if (getenv("RIP_DISABLE_FUSED")) return false;
+    if (options().disable_fused) return false;
     return true;
 }
 
@@ -145,10 +145,7 @@ bool fused_plan_weights(const float *w25, float g[3], float *thr)
 
 static int pick_seg_rows(int out_rows, int n_frames, int n_band_groups, int device, int resident_blocks = 6)
 {
-    if (const char *e = getenv("RIP_FUSED_SEG")) {
-        const int v = atoi(e);
-        if (v > 0) return v < out_rows ? v : out_rows;
-    }
+    if (const int v = options().fused_seg; v > 0) return v < out_rows ? v : out_rows;
     // enough blocks for >= ~3 waves of (SMs x resident blocks), but segments of >= 32 rows (6 warm-up rows
     // each); never more than 256 rows (tail balance).  Measured: 32 4K frames 94..270 rows 416-430 us (flat),
     // 360 rows 500 us; a single 4K frame 32 rows 38 us, 64 rows 46 us, 128 rows 67 us.
@@ -163,7 +160,7 @@ static unsigned long long *g_slow_counter = nullptr;  // set by rip_debug_slow_p
 
 // d_gray_down, per device, filled once by evaluating the reference expression (Comparator.cpp:41)
 // in double on the host for the 16 774 (r,g,b) triples whose 299r+587g+114b is a multiple of 1000.
-static int ensure_gray_table(int device)
+static int ensure_gray_table(int device, cudaStream_t stream)
 {
     static std::mutex mu;
     static bool done[64];
@@ -188,7 +185,10 @@ static int ensure_gray_table(int device)
                 }
         built = true;
     }
-    RIP_CUDA(cudaMemcpyToSymbol(d_gray_down, bits, sizeof(bits)));
+    // stream-ordered before the first kernel that reads the table (the library's streams are non-blocking, so a copy on
+    // the legacy stream would not be); the source is static storage, so a staged pageable copy is safe
+    RIP_CUDA(cudaMemcpyToSymbolAsync(d_gray_down, bits, sizeof(bits), 0, cudaMemcpyHostToDevice, stream));
+    RIP_CUDA(cudaStreamSynchronize(stream));   // once per device: later launches on OTHER streams must see it too
     done[device] = true;
     return RIP_OK;
 }
@@ -244,8 +244,7 @@ static int launch_fused_x2_n(cudaStream_t s, FusedParams p, int n_frames, int fm
 // pixels per lane of the kernel that runs: RIP_FUSED_NPX = 8 | 4 (8 needs W % 8 == 0 and 8/16-byte aligned images)
 static int x2_npx(int W, int cn, const uint8_t *d_in, const uint8_t *d_out)
 {
-    int want = 8;
-    if (const char *e = getenv("RIP_FUSED_NPX")) want = atoi(e) == 4 ? 4 : 8;
+    const int want = options().fused_npx == 4 ? 4 : 8;
     const uintptr_t in_align8 = cn == 4 ? 15u : 7u;   // (1 and 3 channels: 8 pixels are 8 / 24 bytes, loaded as 64-bit words)
     const bool ok8 = (W & 7) == 0 && !(reinterpret_cast<uintptr_t>(d_in) & in_align8) && !(reinterpret_cast<uintptr_t>(d_out) & 7u);
     if (want == 8 && ok8) return 8;
@@ -256,7 +255,7 @@ int launch_fused(cudaStream_t s, const uint8_t *d_in, uint8_t *d_out, int W, int
                  bool with_blur, const float *weights25, int in_row0, int in_rows, int out_row0, int out_rows,
                  int device)
 {
-    if (int rc = ensure_gray_table(device)) return rc;
+    if (int rc = ensure_gray_table(device, s)) return rc;
     FusedParams p;
     memset(&p, 0, sizeof(p));
     p.in = d_in; p.out = d_out; p.W = W; p.H = H;
@@ -338,7 +337,7 @@ __global__ void selftest_gray_x2_kernel(unsigned long long *bad)
 
 int fused_selftest(int device, unsigned long long *checked, unsigned long long *mismatches)
 {
-    if (int rc = ensure_gray_table(device)) return rc;
+    if (int rc = ensure_gray_table(device, nullptr)) return rc;
     unsigned long long *d_bad = nullptr;
     RIP_CUDA(cudaMalloc(&d_bad, sizeof(*d_bad)));
     RIP_CUDA(cudaMemset(d_bad, 0, sizeof(*d_bad)));

@@ -189,13 +189,19 @@ int launch_blur_exact(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, i
         return fail(RIP_EINVAL, "rip_gauss: RGBA buffers must be 4-byte aligned");
     const int half = ksize >> 1;
     const dim3 block(BLUR_TW, BLUR_TH);
-    const dim3 grid((W + BLUR_TW - 1) / BLUR_TW, (out_rows + BLUR_TH - 1) / BLUR_TH, n_frames);
     const size_t smem = (size_t)(BLUR_TW + 2 * half) * (BLUR_TH + 2 * half) * cn;
-    if (cn == 4)
-        blur_exact_kernel<4><<<grid, block, smem, s>>>(src, dst, W, H, src_row0, src_rows, out_row0, out_rows, ksize, wts);
-    else
-        blur_exact_kernel<1><<<grid, block, smem, s>>>(src, dst, W, H, src_row0, src_rows, out_row0, out_rows, ksize, wts);
-    RIP_LAUNCH_CHECK();
+    // frames ride in gridDim.z (<= 65535): batches of tiny frames go out in slabs
+    for (int f0 = 0; f0 < n_frames; f0 += kMaxGridZ) {
+        const int nf = min(n_frames - f0, kMaxGridZ);
+        const dim3 grid((W + BLUR_TW - 1) / BLUR_TW, (out_rows + BLUR_TH - 1) / BLUR_TH, nf);
+        const uint8_t *fs = src + (size_t)f0 * src_rows * W * cn;
+        uint8_t *fd = dst + (size_t)f0 * out_rows * W * cn;
+        if (cn == 4)
+            blur_exact_kernel<4><<<grid, block, smem, s>>>(fs, fd, W, H, src_row0, src_rows, out_row0, out_rows, ksize, wts);
+        else
+            blur_exact_kernel<1><<<grid, block, smem, s>>>(fs, fd, W, H, src_row0, src_rows, out_row0, out_rows, ksize, wts);
+        RIP_LAUNCH_CHECK();
+    }
     return RIP_OK;
 }
 
@@ -267,19 +273,24 @@ sobel_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int W, 
 int launch_sobel(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int H, int n_frames, int fmt,
                  int src_row0, int src_rows, int out_row0, int out_rows)
 {
-    const dim3 grid((W + SOB_TW - 1) / SOB_TW, (out_rows + SOB_TH - 1) / SOB_TH, n_frames), block(256);
+    const dim3 block(256);
+    // frames ride in gridDim.z (<= 65535): batches of tiny frames go out in slabs
+    for (int f0 = 0; f0 < n_frames; f0 += kMaxGridZ) {
+        const dim3 grid((W + SOB_TW - 1) / SOB_TW, (out_rows + SOB_TH - 1) / SOB_TH, min(n_frames - f0, kMaxGridZ));
+        uint8_t *fd = dst + (size_t)f0 * out_rows * W;
 #define RIP_SOBEL_CASE(F, CN, BGR) \
-    case F: sobel_kernel<CN, BGR><<<grid, block, 0, s>>>(src, dst, W, H, src_row0, src_rows, out_row0, out_rows); break;
-    switch (fmt) {
-        RIP_SOBEL_CASE(RIP_FMT_GRAY8, 1, false)
-        RIP_SOBEL_CASE(RIP_FMT_RGB8, 3, false)
-        RIP_SOBEL_CASE(RIP_FMT_BGR8, 3, true)
-        RIP_SOBEL_CASE(RIP_FMT_RGBA8, 4, false)
-        RIP_SOBEL_CASE(RIP_FMT_BGRA8, 4, true)
-    default: return fail(RIP_EINVAL, "rip_sobel: unsupported input format %d", fmt);
-    }
+    case F: sobel_kernel<CN, BGR><<<grid, block, 0, s>>>(src + (size_t)f0 * src_rows * W * CN, fd, W, H, src_row0, src_rows, out_row0, out_rows); break;
+        switch (fmt) {
+            RIP_SOBEL_CASE(RIP_FMT_GRAY8, 1, false)
+            RIP_SOBEL_CASE(RIP_FMT_RGB8, 3, false)
+            RIP_SOBEL_CASE(RIP_FMT_BGR8, 3, true)
+            RIP_SOBEL_CASE(RIP_FMT_RGBA8, 4, false)
+            RIP_SOBEL_CASE(RIP_FMT_BGRA8, 4, true)
+        default: return fail(RIP_EINVAL, "rip_sobel: unsupported input format %d", fmt);
+        }
 #undef RIP_SOBEL_CASE
-    RIP_LAUNCH_CHECK();
+        RIP_LAUNCH_CHECK();
+    }
     return RIP_OK;
 }
 

@@ -132,6 +132,11 @@ void Controller::Cleanup(cl_context context, cl_command_queue commandQueue, cl_p
                          cl_mem *mem_objects, int num_mem_objects)
 {
     (void)sampler; (void)mem_objects; (void)num_mem_objects;   // device buffers are cached inside the contexts
+    // frames still in flight are collected (their contexts are about to go), pinned containers released
+    for (auto &kv : m_pending) rip_collect(kv.second.ticket, nullptr);
+    m_pending.clear();
+    for (void *p : m_pinned) rip_host_unregister(p);
+    m_pinned.clear();
     if (kernel) rip_kernel_release(kernel);
     if (program) rip_module_release(program);
     if (commandQueue) {
@@ -158,6 +163,48 @@ void Controller::_appendProfile(const uint64_t prof_ns[6], std::vector<cl_ulong>
     for (int i = 0; i < 6; i++) profiling_events->push_back(prof_ns[i]);
 }
 
+// bytes of one input frame in `fmt` (NV12: the luma plane followed by the half-height chroma plane), 0 = bad format / shape
+static size_t in_frame_bytes(int fmt, int width, int height)
+{
+    const size_t px = (size_t)width * height;
+    switch (fmt) {
+    case RIP_FMT_GRAY8: return px;
+    case RIP_FMT_NV12: return (height & 1) ? 0 : px * 3 / 2;
+    case RIP_FMT_RGB8: case RIP_FMT_BGR8: return px * 3;
+    case RIP_FMT_RGBA8: case RIP_FMT_BGRA8: return px * 4;
+    default: return 0;
+    }
+}
+
+// Validates the shapes and sizes the result container: resized in place (no zero-filled temporary per call), unless it
+// aliases the input.  Returns the output pointer, or nullptr after logging.
+static unsigned char *prepare_output(const rip_op_desc &desc, const unsigned char *in, size_t in_bytes, std::vector<unsigned char> *output_data,
+                                     int width, int height, int n_frames, Logger &logger, const char *what)
+{
+    size_t out_frame = 0;
+    if (width <= 0 || height <= 0 || n_frames <= 0 || rip_out_bytes_per_frame(&desc, width, height, &out_frame) != RIP_OK) {
+        logger.log(std::string(what) + ": bad shape or operation", Logger::LogLevel::ERROR);
+        return nullptr;
+    }
+    const size_t in_frame = in_frame_bytes(desc.in_format, width, height);
+    if (in_frame == 0) {
+        logger.log(std::string(what) + ": unsupported input format (NV12 needs an even height)", Logger::LogLevel::ERROR);
+        return nullptr;
+    }
+    if (in_bytes != (size_t)-1 && in_bytes < in_frame * (size_t)n_frames) {
+        logger.log(std::string(what) + ": input holds fewer bytes than width*height*frames of its format need", Logger::LogLevel::ERROR);
+        return nullptr;
+    }
+    const size_t need = out_frame * (size_t)n_frames;
+    const unsigned char *ob = output_data->data(), *oe = ob + output_data->capacity();
+    if (ob && in + in_frame * (size_t)n_frames > ob && in < oe) {   // output vector overlaps the input: do not resize under the reader
+        logger.log(std::string(what) + ": input and output containers overlap", Logger::LogLevel::ERROR);
+        return nullptr;
+    }
+    output_data->resize(need);   // same observable result as the reference's assignment (RT/src/Controller.cpp:510,605)
+    return output_data->data();
+}
+
 void Controller::_run(const rip_op_desc &desc, rip_ctx *ctx, std::vector<cl_ulong> *profiling_events, const unsigned char *in,
                       size_t in_bytes, std::vector<unsigned char> *output_data, int width, int height, int n_frames, bool banded,
                       Logger &logger, const char *what)
@@ -166,27 +213,17 @@ void Controller::_run(const rip_op_desc &desc, rip_ctx *ctx, std::vector<cl_ulon
         logger.log(std::string(what) + ": NULL context, input or output", Logger::LogLevel::ERROR);
         return;
     }
-    size_t out_frame = 0, in_frame = 0;
-    if (rip_out_bytes_per_frame(&desc, width, height, &out_frame) != RIP_OK) {
-        logger.log(std::string(what) + ": " + rip_last_error_string(), Logger::LogLevel::ERROR);
-        return;
-    }
-    const int cn = desc.in_format == RIP_FMT_GRAY8 ? 1 : (desc.in_format == RIP_FMT_RGB8 || desc.in_format == RIP_FMT_BGR8) ? 3 : 4;
-    in_frame = (size_t)width * height * cn;
-    if (in_bytes < in_frame * (size_t)n_frames) {
-        logger.log(std::string(what) + ": input holds fewer than width*height*channels*frames bytes", Logger::LogLevel::ERROR);
-        return;
-    }
-    std::vector<unsigned char> out(out_frame * (size_t)n_frames);
+    unsigned char *out = prepare_output(desc, in, in_bytes, output_data, width, height, n_frames, logger, what);
+    if (!out) return;
     uint64_t prof[6] = {0, 0, 0, 0, 0, 0};
-    const int rc = banded ? rip_process_host_banded(ctx, &desc, in, out.data(), width, height, prof)
-                          : rip_process_host(ctx, &desc, in, out.data(), width, height, n_frames, prof);
+    const int rc = banded ? rip_process_host_banded(ctx, &desc, in, out, width, height, prof)
+                          : rip_process_host(ctx, &desc, in, out, width, height, n_frames, prof);
     if (rc != RIP_OK) {
         logger.log(std::string(what) + " failed: " + rip_last_error_string(), Logger::LogLevel::ERROR);
+        output_data->clear();
         return;
     }
     _appendProfile(prof, profiling_events);
-    *output_data = std::move(out);   // the reference assigns, it does not resize in place (RT/src/Controller.cpp:510,605)
 }
 
 void Controller::PerformCLImageGrayscaling(cl_context *context, cl_command_queue *command_queue, cl_kernel *kernel,
@@ -251,7 +288,7 @@ static bool desc_of_method(const std::string &method, int in_format, int kernel_
 
 void Controller::PerformBatch(const std::string &method, cl_context *context, std::vector<cl_ulong> *profiling_events,
                               const unsigned char *frames, int n_frames, std::vector<unsigned char> *output_data, cl_int &width,
-                              cl_int &height, Logger &logger, int in_format, int kernel_size, float kernel_sigma)
+                              cl_int &height, Logger &logger, int in_format, int kernel_size, float kernel_sigma, size_t frames_bytes)
 {
     std::vector<float> w;
     if (method == "GAUSSIAN" || method == "FUSED") w = _GenerateGausianKernel(kernel_size, kernel_sigma);
@@ -260,7 +297,7 @@ void Controller::PerformBatch(const std::string &method, cl_context *context, st
         logger.log("PerformBatch: unknown method " + method, Logger::LogLevel::ERROR);
         return;
     }
-    _run(d, context && *context ? (*context)->ctx : nullptr, profiling_events, frames, (size_t)-1, output_data, width, height, n_frames, false,
+    _run(d, context && *context ? (*context)->ctx : nullptr, profiling_events, frames, frames_bytes ? frames_bytes : (size_t)-1, output_data, width, height, n_frames, false,
          logger, "PerformBatch");
 }
 
@@ -277,4 +314,85 @@ void Controller::PerformBanded(const std::string &method, cl_context *context, s
     }
     _run(d, context && *context ? (*context)->ctx : nullptr, profiling_events, input_data ? input_data->data() : nullptr,
          input_data ? input_data->size() : 0, output_data, width, height, 1, true, logger, "PerformBanded");
+}
+
+// ---- [new] asynchronous per-frame form --------------------------------------------------------------------------------
+// The reference's frame loop (RealtimeImageProcessing.cpp:325-418) calls PerformOpenCL once per camera frame and blocks
+// three times inside it.  SubmitFrame queues the frame on the context's device worker and returns at once; CollectFrame
+// waits for it.  With two or three frames in flight the upload of frame i+1, the kernel of frame i and the download of
+// frame i-1 overlap.  input_data must stay untouched and output_data unread until CollectFrame(handle) has returned.
+int Controller::SubmitFrame(const std::string &method, cl_command_queue *command_queue, std::vector<unsigned char> *input_data,
+                            std::vector<unsigned char> *output_data, cl_int &width, cl_int &height, Logger &logger, int in_format,
+                            int kernel_size, float kernel_sigma)
+{
+    rip_ctx *ctx = command_queue && *command_queue ? (*command_queue)->ctx : nullptr;
+    if (!ctx || !input_data || !output_data) {
+        logger.log("SubmitFrame: NULL queue, input or output", Logger::LogLevel::ERROR);
+        return 0;
+    }
+    std::vector<float> w;
+    if (method == "GAUSSIAN" || method == "FUSED") {
+        if (kernel_size < 1 || !(kernel_size & 1) || kernel_size > RIP_MAX_KSIZE) {
+            logger.log("SubmitFrame: kernel size must be odd and in 1.." + std::to_string(RIP_MAX_KSIZE), Logger::LogLevel::ERROR);
+            return 0;
+        }
+        w = _GenerateGausianKernel(kernel_size, kernel_sigma);
+    }
+    rip_op_desc d;
+    if (!desc_of_method(method, in_format, kernel_size, w.data(), &d)) {
+        logger.log("SubmitFrame: unknown method " + method, Logger::LogLevel::ERROR);
+        return 0;
+    }
+    unsigned char *out = prepare_output(d, input_data->data(), input_data->size(), output_data, width, height, 1, logger, "SubmitFrame");
+    if (!out) return 0;
+    rip_ticket *t = nullptr;
+    if (rip_submit(ctx, &d, input_data->data(), out, width, height, 1, RIP_SUBMIT_PROFILE, &t) != RIP_OK) {   // (copies d and w)
+        logger.log(std::string("SubmitFrame failed: ") + rip_last_error_string(), Logger::LogLevel::ERROR);
+        output_data->clear();
+        return 0;
+    }
+    const int handle = ++m_next_handle > 0 ? m_next_handle : (m_next_handle = 1);
+    m_pending[handle] = Pending{t, output_data};
+    return handle;
+}
+
+bool Controller::CollectFrame(int handle, std::vector<cl_ulong> *profiling_events, Logger &logger)
+{
+    auto it = m_pending.find(handle);
+    if (it == m_pending.end()) {
+        logger.log("CollectFrame: unknown handle " + std::to_string(handle), Logger::LogLevel::ERROR);
+        return false;
+    }
+    const Pending p = it->second;
+    m_pending.erase(it);
+    uint64_t prof[6] = {0, 0, 0, 0, 0, 0};
+    if (rip_collect(p.ticket, prof) != RIP_OK) {
+        logger.log(std::string("CollectFrame failed: ") + rip_last_error_string(), Logger::LogLevel::ERROR);
+        p.output->clear();
+        return false;
+    }
+    _appendProfile(prof, profiling_events);
+    return true;
+}
+
+// [new] page-lock a container the caller reuses across calls (the iteration loop hands the same input_data to PerformCL*
+// NUMBER_OF_ITERATIONS times), so that the pipeline copies it by DMA without a staging copy.  The container must not
+// reallocate while it is pinned; Cleanup() releases whatever is still pinned.
+bool Controller::PinHostBuffer(std::vector<unsigned char> *buffer)
+{
+    if (!buffer || buffer->empty()) return false;
+    if (rip_host_register(buffer->data(), buffer->size()) != RIP_OK) return false;
+    m_pinned.push_back(buffer->data());
+    return true;
+}
+
+void Controller::UnpinHostBuffer(std::vector<unsigned char> *buffer)
+{
+    if (!buffer) return;
+    for (size_t i = 0; i < m_pinned.size(); i++)
+        if (m_pinned[i] == buffer->data()) {
+            rip_host_unregister(m_pinned[i]);
+            m_pinned.erase(m_pinned.begin() + i);
+            return;
+        }
 }

@@ -15,6 +15,7 @@
 // Additions beyond the reference are marked [new].
 #pragma once
 
+#include <map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -64,11 +65,22 @@ public:
     // blocks of frames per device, no inter-device traffic).  method: "GRAYSCALE" | "EDGE" | "GAUSSIAN" | "FUSED".
     void PerformBatch(const std::string &method, cl_context *context, std::vector<cl_ulong> *profiling_events,
                       const unsigned char *frames, int n_frames, std::vector<unsigned char> *output_data, cl_int &width,
-                      cl_int &height, Logger &logger, int in_format = RIP_FMT_RGBA8, int kernel_size = 5, float kernel_sigma = 1.0f);
+                      cl_int &height, Logger &logger, int in_format = RIP_FMT_RGBA8, int kernel_size = 5, float kernel_sigma = 1.0f,
+                      size_t frames_bytes = 0 /* bytes behind `frames` (0 = not checked) */);
     // [new] one large frame split into row bands with halo, one band per device of the context (EDGE, FUSED)
     void PerformBanded(const std::string &method, cl_context *context, std::vector<cl_ulong> *profiling_events,
                        std::vector<unsigned char> *input_data, std::vector<unsigned char> *output_data, cl_int &width,
                        cl_int &height, Logger &logger, int in_format = RIP_FMT_RGBA8, int kernel_size = 5, float kernel_sigma = 1.0f);
+    // [new] asynchronous per-frame form of the three operations (+ "FUSED"): SubmitFrame queues one frame and returns a handle
+    // (0 = rejected, logged) at once; CollectFrame blocks until that frame is in output_data.  Frames complete in submission
+    // order; with 2-3 frames in flight upload, kernel and download of consecutive frames overlap.
+    int SubmitFrame(const std::string &method, cl_command_queue *command_queue, std::vector<unsigned char> *input_data,
+                    std::vector<unsigned char> *output_data, cl_int &width, cl_int &height, Logger &logger, int in_format = RIP_FMT_RGBA8,
+                    int kernel_size = 5, float kernel_sigma = 1.0f);
+    bool CollectFrame(int handle, std::vector<cl_ulong> *profiling_events, Logger &logger);
+    // [new] page-lock / release a container that is reused across calls (copied by DMA without a staging copy)
+    bool PinHostBuffer(std::vector<unsigned char> *buffer);
+    void UnpinHostBuffer(std::vector<unsigned char> *buffer);
     // [new] restrict GetDevices() to these CUDA ordinals (default: all visible devices)
     void SetDevices(const std::vector<int> &ordinals);
 
@@ -80,6 +92,13 @@ private:
     cl_uint num_platforms, num_devices;
     cl_bool m_image_support;
     std::vector<int> m_ordinals;
+    struct Pending {
+        rip_ticket *ticket;
+        std::vector<unsigned char> *output;
+    };
+    std::map<int, Pending> m_pending;
+    int m_next_handle = 0;
+    std::vector<void *> m_pinned;
 
     void _appendProfile(const uint64_t prof_ns[6], std::vector<cl_ulong> *profiling_events);
     void _run(const rip_op_desc &desc, rip_ctx *ctx, std::vector<cl_ulong> *profiling_events, const unsigned char *in, size_t in_bytes,

@@ -169,3 +169,45 @@ std::vector<unsigned char> ProgramHandler::PerformOpenCL(Controller &controller,
     Dispatch(controller, method, context, command_queue, kernel, &events, &input_data, &output, width, height, logger);
     return output;
 }
+
+int ProgramHandler::SubmitOpenCL(Controller &controller, const cv::Mat &input_frame, cl_command_queue *command_queue, cl_int &width,
+                                 cl_int &height, Logger &logger, std::string method)
+{
+    std::unique_ptr<FrameSlot> slot;
+    if (!m_free_slots.empty()) {
+        slot = std::move(m_free_slots.back());
+        m_free_slots.pop_back();
+    } else {
+        slot.reset(new FrameSlot());
+    }
+    cl_int w = 0, h = 0;
+    GetMatrix(input_frame, &slot->in, &w, &h, logger);
+    if (slot->in.empty()) return 0;
+    if (width != 0 && height != 0 && (w != width || h != height)) {
+        logger.log("Frame is " + std::to_string(w) + "x" + std::to_string(h) + " but " + std::to_string(width) + "x" + std::to_string(height) +
+                       " was announced", Logger::LogLevel::ERROR);
+        return 0;
+    }
+    width = w;
+    height = h;
+    const int handle = controller.SubmitFrame(method, command_queue, &slot->in, &slot->out, width, height, logger, RIP_FMT_RGBA8,
+                                              GAUSSIAN_KERNEL_SIZE, GAUSSIAN_SIGMA);
+    if (handle == 0) return 0;
+    m_frames[handle] = std::move(slot);
+    return handle;
+}
+
+std::vector<unsigned char> ProgramHandler::CollectOpenCL(Controller &controller, int handle, Logger &logger, std::vector<cl_ulong> *events)
+{
+    std::vector<unsigned char> output;
+    auto it = m_frames.find(handle);
+    if (it == m_frames.end()) {
+        logger.log("CollectOpenCL: unknown handle " + std::to_string(handle), Logger::LogLevel::ERROR);
+        return output;
+    }
+    std::unique_ptr<FrameSlot> slot = std::move(it->second);
+    m_frames.erase(it);
+    if (controller.CollectFrame(handle, events, logger)) output = slot->out;   // (the slot keeps its capacity for the next frame)
+    if (m_free_slots.size() < 8) m_free_slots.push_back(std::move(slot));
+    return output;
+}

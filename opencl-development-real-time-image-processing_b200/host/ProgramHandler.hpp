@@ -5,6 +5,7 @@
 #pragma once
 
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -34,7 +35,20 @@ public:
                                              cl_command_queue *command_queue, cl_kernel *kernel, cl_int &width, cl_int &height, Logger &logger,
                                              std::string method);
 
+    // [new] streaming form of the per-frame variant: SubmitOpenCL converts the frame, queues it and returns a handle (0 = rejected)
+    // at once; CollectOpenCL blocks until that frame is done and returns its output (and, if `events` is given, the six
+    // profiling values).  The frame loop of RealtimeImageProcessing.cpp:325-418 with two or three frames in flight overlaps
+    // the upload of frame i+1, the kernel of frame i and the download of frame i-1.  Frames complete in submission order.
+    int SubmitOpenCL(Controller &controller, const cv::Mat &input_frame, cl_command_queue *command_queue, cl_int &width, cl_int &height,
+                     Logger &logger, std::string method);
+    std::vector<unsigned char> CollectOpenCL(Controller &controller, int handle, Logger &logger, std::vector<cl_ulong> *events = nullptr);
+
 private:
+    struct FrameSlot {
+        std::vector<unsigned char> in, out;
+    };
+    std::map<int, std::unique_ptr<FrameSlot>> m_frames;   // frames in flight, by Controller handle
+    std::vector<std::unique_ptr<FrameSlot>> m_free_slots; // recycled containers (no allocation per frame in steady state)
     bool LOG_EVENTS;
     bool DISPLAY_IMAGES;
     bool DISPLAY_TERMINAL_RESULTS;

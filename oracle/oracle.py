@@ -154,3 +154,30 @@ def ocl_blur_rgba(rgba: np.ndarray, ksize: int, weights: np.ndarray) -> np.ndarr
     out = np.empty((h, w, 4), np.uint8)
     _chk(lib().rip_oracle_ocl_blur_rgba(_u8(rgba), w, h, ksize, _f32(weights), _u8(out)), "ocl_blur")
     return out
+
+
+# ---- oracle/_ref: the REFERENCE's own weight generator, compiled from /root/reference (oracle/Makefile `ref`) ----
+_REF_PATH = os.path.join(_HERE, "_ref", "librip_ref_weights.so")
+_ref = None
+
+
+def build_ref() -> str | None:
+    """(Re)build oracle/_ref where the reference tree exists; elsewhere keep the prebuilt file.  Returns its path
+    or None when there is neither."""
+    if os.path.isdir("/root/reference/src/GaussianBlur"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return _REF_PATH if os.path.exists(_REF_PATH) else None
+
+
+def ref_gauss_weights(ksize: int, sigma: float) -> np.ndarray | None:
+    """Controller::_GenerateGausianKernel of the reference itself (src/GaussianBlur/src/Controller.cpp:342-362,395-417),
+    or None when oracle/_ref has not been built."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(_REF_PATH):
+            return None
+        _ref = C.CDLL(_REF_PATH)
+        _ref.rip_ref_gauss_weights.argtypes = [C.c_int, C.c_float, C.POINTER(C.c_float)]
+    out = np.empty((ksize, ksize), np.float32)
+    _chk(_ref.rip_ref_gauss_weights(ksize, C.c_float(sigma), _f32(out)), "ref_gauss_weights")
+    return out

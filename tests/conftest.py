@@ -70,3 +70,19 @@ def synth_frame(kind: str, h: int, w: int, seed: int, cn: int = 3) -> np.ndarray
         img += rng.integers(-2, 3, img.shape)
         return np.clip(img, 0, 255).astype(np.uint8)
     raise ValueError(kind)
+
+
+@pytest.fixture
+def opt():
+    """Set a librip_cuda experiment switch (rip_debug_set_option) for one test; every switch touched is put back to 0
+    afterwards."""
+    import rip_b200 as rip
+    touched = []
+
+    def _set(name, value):
+        touched.append(name)
+        rip.set_option(name, value)
+
+    yield _set
+    for name in touched:
+        rip.set_option(name, 0)

@@ -125,6 +125,54 @@ int main(int argc, char **argv)
         for (int i = 0; ok && i < 3; i++) ok = !memcmp(out.data() + (size_t)i * cpu.total(), cpu.data, cpu.total());
         std::printf("PerformBatch FUSED x3 on %zu device(s): %s\n", devices.size(), ok ? "exact" : "MISMATCH");
         if (!ok) failures++;
+        // [new] NV12 (the reference's camera format, RealtimeImageProcessing.cpp:153): the luma plane is the gray image
+        {
+            double t2 = 0;
+            cv::Mat gray = comparator.PerformCPU_Grayscaling(rgba, false, t2, logger);
+            const int hh = gray.rows & ~1, ww = gray.cols;
+            std::vector<unsigned char> nv12((size_t)ww * hh * 3 / 2, 128), out_nv;
+            memcpy(nv12.data(), gray.data, (size_t)ww * hh);
+            cv::Mat luma(hh, ww, cv::CV_8UC1, nv12.data());
+            cv::Mat cpu_nv = comparator.PerformCPU_EdgeDetection(comparator.PerformCPU_GaussianBlur(luma, ksize, sigma, t2, logger), t2, logger);
+            cl_command_queue q = controller.CreateCommandQueue(context, devices[0]);
+            cl_int w2 = ww, h2 = hh;
+            int ks = ksize;
+            float sg = sigma;
+            controller.PerformFused(ks, sg, &context, &q, nullptr, &events, &nv12, &out_nv, w2, h2, logger, RIP_FMT_NV12);
+            const bool ok_nv = out_nv.size() == (size_t)ww * hh && !memcmp(out_nv.data(), cpu_nv.data, out_nv.size());
+            std::printf("PerformFused NV12 %dx%d: %s\n", ww, hh, ok_nv ? "exact" : "MISMATCH");
+            if (!ok_nv) failures++;
+            // a short NV12 buffer must be rejected, not read past its end
+            std::vector<unsigned char> small((size_t)ww * hh, 0), out_small;
+            controller.PerformFused(ks, sg, &context, &q, nullptr, &events, &small, &out_small, w2, h2, logger, RIP_FMT_NV12);
+            if (!out_small.empty()) { std::printf("short NV12 buffer was accepted\n"); failures++; }
+            controller.Cleanup(0, q);
+        }
+        // [new] streaming form: six frames, three in flight, every result equal to the blocking call's
+        {
+            cl_context c2 = 0; cl_command_queue q2 = 0; cl_program p2 = 0; cl_kernel k2 = 0;
+            handler.InitOpenCL(controller, &c2, &q2, &p2, &k2, "FUSED", logger);
+            cl_int w2 = rgba.cols, h2 = rgba.rows;
+            std::vector<unsigned char> want = handler.PerformOpenCL(controller, rgba, &c2, &q2, &k2, w2, h2, logger, "FUSED");
+            std::vector<int> inflight;
+            int got = 0;
+            bool ok_s = !want.empty();
+            for (int i = 0; i < 6 && ok_s; i++) {
+                const int hnd = handler.SubmitOpenCL(controller, rgba, &q2, w2, h2, logger, "FUSED");
+                if (!hnd) { ok_s = false; break; }
+                inflight.push_back(hnd);
+                if (inflight.size() == 3) {
+                    std::vector<cl_ulong> ev;
+                    ok_s = handler.CollectOpenCL(controller, inflight.front(), logger, &ev) == want && ev.size() == 6;
+                    inflight.erase(inflight.begin());
+                    got++;
+                }
+            }
+            for (int hnd : inflight) { ok_s = (handler.CollectOpenCL(controller, hnd, logger) == want) && ok_s; got++; }
+            std::printf("SubmitOpenCL/CollectOpenCL x%d: %s\n", got, ok_s && got == 6 ? "exact" : "MISMATCH");
+            if (!ok_s || got != 6) failures++;
+            controller.Cleanup(c2, q2, p2, k2);
+        }
         controller.Cleanup(context);
         files.WriteResultsToCSV(work + "/results.csv", results);
     }

@@ -126,30 +126,30 @@ def _adversarial_rgba(h, w):
 
 
 @pytest.mark.parametrize("k,sigma", [(5, 1.0), (5, 1.5), (9, 2.5), (17, 6.0)])
-def test_blur_separable_kernel_equals_exact_kernel_and_oracle(ctx, oracle, k, sigma, monkeypatch):
+def test_blur_separable_kernel_equals_exact_kernel_and_oracle(ctx, oracle, k, sigma, opt):
     """The separable guard-band kernel (default) and the reference-order kernel (RIP_BLUR_EXACT) must agree bit for bit."""
     w = rip.gauss_weights(k, sigma)
     imgs = [synth_frame("uniform", 70, 101, 3, 4), synth_frame("smooth", 33, 64, 4, 4)] + _adversarial_rgba(37, 45)
     for i, img in enumerate(imgs):
         want = oracle.blur(img, k, weights=w, threads=0)
-        monkeypatch.delenv("RIP_BLUR_EXACT", raising=False)
+        opt("RIP_BLUR_EXACT", 0)
         _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), want, f"separable blur K={k} frame {i}")
         g = np.ascontiguousarray(img[..., 0])
         _eq(ctx.process(g, rip.OP_GAUSSIAN, rip.FMT_GRAY8, ksize=k, weights=w), oracle.blur(g, k, weights=w, threads=0),
             f"separable blur gray K={k} frame {i}")
-        monkeypatch.setenv("RIP_BLUR_EXACT", "1")
+        opt("RIP_BLUR_EXACT", 1)
         _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), want, f"exact blur K={k} frame {i}")
         if k == 5:   # 5x5 RGBA has two guard-band kernels: streaming (large inputs) and tiled; force each
-            monkeypatch.delenv("RIP_BLUR_EXACT", raising=False)
+            opt("RIP_BLUR_EXACT", 0)
             for force in ("RIP_BLUR_TILED", "RIP_BLUR_STREAM"):
-                monkeypatch.setenv(force, "1")
+                opt(force, 1)
                 _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), want, f"{force} blur frame {i}")
-                monkeypatch.delenv(force, raising=False)
+                opt(force, 0)
 
 
 @pytest.mark.parametrize("shape", [(3, 130, 250), (2, 67, 61), (1, 40, 1000), (5, 33, 64)])
-def test_blur_streaming_kernel_batches_and_ragged_widths(ctx, oracle, shape, monkeypatch):
-    monkeypatch.setenv("RIP_BLUR_STREAM", "1")
+def test_blur_streaming_kernel_batches_and_ragged_widths(ctx, oracle, shape, opt):
+    opt("RIP_BLUR_STREAM", 1)
     n, h, wd = shape
     for sigma in (1.0, 1.5):
         w = rip.gauss_weights(5, sigma)
@@ -203,8 +203,8 @@ def test_sobel_gray_input_matches_opencv_goldens(ctx, golden_cv2_sobel, golden_i
 @pytest.mark.parametrize("shape", [(2, 4), (2, 8), (5, 12), (37, 120), (37, 124), (64, 128), (33, 244), (75, 75), (19, 241),
                                    (2, 16), (31, 240), (17, 256), (40, 496)])
 @pytest.mark.parametrize("fmt,cn,npx", [(rip.FMT_RGB8, 3, 8), (rip.FMT_RGBA8, 4, 8), (rip.FMT_BGR8, 3, 8), (rip.FMT_RGB8, 3, 4), (rip.FMT_RGBA8, 4, 4)])
-def test_sobel_colour_input(ctx, oracle, shape, fmt, cn, npx, monkeypatch):
-    monkeypatch.setenv("RIP_FUSED_NPX", str(npx))  # pixels per lane of the fused kernel (8 where the width allows it)
+def test_sobel_colour_input(ctx, oracle, shape, fmt, cn, npx, opt):
+    opt("RIP_FUSED_NPX", npx)  # pixels per lane of the fused kernel (8 where the width allows it)
     img = synth_frame("uniform", shape[0], shape[1], 21, cn)
     g = oracle.gray(img, oracle.BGR if fmt == rip.FMT_BGR8 else oracle.RGB)
     _eq(ctx.process(img, rip.OP_EDGE, fmt), oracle.sobel(g), f"sobel colour {shape} cn={cn}")
@@ -212,10 +212,10 @@ def test_sobel_colour_input(ctx, oracle, shape, fmt, cn, npx, monkeypatch):
 
 @pytest.mark.parametrize("shape", [(2, 8), (5, 12), (37, 120), (64, 128), (33, 244), (75, 75), (40, 496), (70, 720)])
 @pytest.mark.parametrize("npx", [8, 4])
-def test_gray_and_nv12_input_edge_and_fused(ctx, oracle, shape, npx, monkeypatch):
+def test_gray_and_nv12_input_edge_and_fused(ctx, oracle, shape, npx, opt):
     """GRAY8 frames, and NV12 frames whose luma plane is the image: Sobel and blur->Sobel on the
     given gray, through the fused kernel where the shape allows it and the staged kernels elsewhere."""
-    monkeypatch.setenv("RIP_FUSED_NPX", str(npx))
+    opt("RIP_FUSED_NPX", npx)
     h, w = shape
     n = 3
     rng = np.random.default_rng(77)
@@ -253,8 +253,8 @@ FUSED_SHAPES = [(2, 4), (3, 8), (7, 12), (16, 120), (40, 124), (9, 128), (70, 24
 
 @pytest.mark.parametrize("shape", FUSED_SHAPES)
 @pytest.mark.parametrize("kind,npx", [("uniform", 8), ("smooth", 8), ("uniform", 4)])
-def test_fused_single_kernel_path(ctx, oracle, shape, kind, npx, monkeypatch):
-    monkeypatch.setenv("RIP_FUSED_NPX", str(npx))
+def test_fused_single_kernel_path(ctx, oracle, shape, kind, npx, opt):
+    opt("RIP_FUSED_NPX", npx)
     img = synth_frame(kind, shape[0], shape[1], 31)
     w = rip.gauss_weights(5, 1.0)
     _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w, threads=0),
@@ -263,8 +263,8 @@ def test_fused_single_kernel_path(ctx, oracle, shape, kind, npx, monkeypatch):
 
 @pytest.mark.parametrize("fmt,cn,order", [(rip.FMT_RGBA8, 4, "RGB"), (rip.FMT_BGR8, 3, "BGR"), (rip.FMT_BGRA8, 4, "BGR")])
 @pytest.mark.parametrize("sigma,npx", [(1.0, 8), (1.5, 8), (1.5, 4)])
-def test_fused_formats_and_sigmas(ctx, oracle, fmt, cn, order, sigma, npx, monkeypatch):
-    monkeypatch.setenv("RIP_FUSED_NPX", str(npx))
+def test_fused_formats_and_sigmas(ctx, oracle, fmt, cn, order, sigma, npx, opt):
+    opt("RIP_FUSED_NPX", npx)
     img = synth_frame("smooth", 97, 248, 41, cn)
     w = rip.gauss_weights(5, sigma)
     want = oracle.fused(img, 5, weights=w, order=oracle.BGR if order == "BGR" else oracle.RGB)
@@ -310,7 +310,7 @@ def test_fused_adversarial_frames(ctx, oracle, sigma):
     _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w), "fused colour ramps")
 
 
-def test_fused_8_and_4_pixel_kernels_agree(oracle, monkeypatch):
+def test_fused_8_and_4_pixel_kernels_agree(oracle, opt):
     """The 4-pixels-per-lane kernel (fallback for widths that are not multiples of 8) must match on an 8-capable shape too."""
     h, wd = 120, 496
     img = synth_frame("uniform", h, wd, 77)
@@ -320,7 +320,7 @@ def test_fused_8_and_4_pixel_kernels_agree(oracle, monkeypatch):
     d_out = rip.DeviceBuffer(h * wd)
     outs = []
     for npx in (8, 4):
-        monkeypatch.setenv("RIP_FUSED_NPX", str(npx))
+        opt("RIP_FUSED_NPX", npx)
         rip.lib().rip_memset_device_async(0, d_out.ptr, 0, h * wd, None)
         rip.fused_dev(d_in.ptr, d_out.ptr, wd, h, 1, rip.FMT_RGB8, 5, w)
         outs.append(d_out.download((h, wd)))
@@ -360,8 +360,8 @@ def test_fused_guard_band_statistics():
 
 
 @pytest.mark.parametrize("wd,npx", [(364, 4), (368, 8), (368, 4)])
-def test_fused_row_bands_equal_whole_frame(ctx, oracle, wd, npx, monkeypatch):
-    monkeypatch.setenv("RIP_FUSED_NPX", str(npx))
+def test_fused_row_bands_equal_whole_frame(ctx, oracle, wd, npx, opt):
+    opt("RIP_FUSED_NPX", npx)
     h = 200
     img = synth_frame("uniform", h, wd, 81)
     w = rip.gauss_weights(5, 1.0)

@@ -19,7 +19,8 @@ ap.add_argument("--w", type=int, default=3840)
 ap.add_argument("--h", type=int, default=2160)
 ap.add_argument("--launches", type=int, default=4)
 ap.add_argument("--kind", default="uniform")
-ap.add_argument("--fmt", default="rgb", help="rgb | gray | nv12 (gray / nv12: the input is the luma plane)")
+ap.add_argument("--fmt", default="rgb", help="rgb | rgba | gray | nv12 (gray / nv12: the input is the luma plane)")
+ap.add_argument("--sigma", type=float, default=1.0)
 a = ap.parse_args()
 
 rng = np.random.default_rng(1)
@@ -27,17 +28,30 @@ if a.kind == "uniform":
     one = rng.integers(0, 256, (a.h, a.w, 3), dtype=np.uint8)
 elif a.kind == "zero":
     one = np.zeros((a.h, a.w, 3), np.uint8)
+elif a.kind == "smooth":
+    yy, xx = np.mgrid[0:a.h, 0:a.w]
+    sm = (128 + 60 * np.sin(xx / 97.0) + 50 * np.cos(yy / 61.0) + rng.integers(-2, 3, (a.h, a.w))).clip(0, 255).astype(np.uint8)
+    one = np.ascontiguousarray(np.stack([sm, np.roll(sm, 7, 1), np.roll(sm, 13, 0)], -1))
+elif a.kind == "letterbox":   # 25 % black bars above and below textured content
+    one = rng.integers(0, 256, (a.h, a.w, 3), dtype=np.uint8)
+    one[: a.h // 8] = 0
+    one[-(a.h // 8):] = 0
+elif a.kind == "halfflat":    # half of the frame is a clipped (constant) region
+    one = rng.integers(0, 256, (a.h, a.w, 3), dtype=np.uint8)
+    one[:, : a.w // 2] = 255
 else:
     one = np.full((a.h, a.w, 3), 77, np.uint8)
 if a.fmt == "gray":
     one = np.ascontiguousarray(one[..., 0])
 elif a.fmt == "nv12":
     one = np.ascontiguousarray(np.concatenate([one[..., 0], one[: a.h // 2, :, 1]], axis=0))
-FMT = {"rgb": rip.FMT_RGB8, "gray": rip.FMT_GRAY8, "nv12": rip.FMT_NV12}[a.fmt]
+elif a.fmt == "rgba":
+    one = np.ascontiguousarray(np.concatenate([one, np.full((a.h, a.w, 1), 255, np.uint8)], -1))
+FMT = {"rgb": rip.FMT_RGB8, "rgba": rip.FMT_RGBA8, "gray": rip.FMT_GRAY8, "nv12": rip.FMT_NV12}[a.fmt]
 frames = np.stack([np.roll(one, i, axis=1) for i in range(a.frames)])
 d_in = rip.DeviceBuffer(frames.nbytes).upload(frames)
 d_out = rip.DeviceBuffer(a.frames * a.h * a.w * 4)
-w = rip.gauss_weights(5, 1.0)
+w = rip.gauss_weights(5, a.sigma)
 def launch():
     if a.op == "fused":
         rip.fused_dev(d_in.ptr, d_out.ptr, a.w, a.h, a.frames, FMT, 5, w)
@@ -59,5 +73,6 @@ for i in range(max(1, a.launches - 1)):
 times.sort()
 ns = times[len(times) // 2]
 px = a.frames * a.h * a.w
-print(f"{a.op} {a.frames}x{a.w}x{a.h}: median {ns/1e3:.1f} us (min {times[0]/1e3:.1f}, max {times[-1]/1e3:.1f}, n={len(times)}), "
-      f"{px/ns*1e3:.0f} Mpx/s, {px*(4 if a.fmt == 'rgb' else 2)/ns:.0f} GB/s algorithmic")
+bpp = {"rgb": 4, "rgba": 5, "gray": 2, "nv12": 2}[a.fmt]
+print(f"{a.op} {a.fmt} {a.kind} {a.frames}x{a.w}x{a.h}: median {ns/1e3:.1f} us (min {times[0]/1e3:.1f}, max {times[-1]/1e3:.1f}, n={len(times)}), "
+      f"{px/ns*1e3:.0f} Mpx/s, {px*bpp/ns:.0f} GB/s algorithmic")
