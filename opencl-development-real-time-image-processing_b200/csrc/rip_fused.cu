@@ -65,11 +65,8 @@ struct FusedParams {
 // Exact gray (Comparator.cpp:41).  With t = 299r + 587g + 114b the real value is t/1000; off the
 // multiples of 1000 the reference's double expression truncates to q = floor(t/1000) (it is >= 1e-3
 // away from an integer, the double rounding error is < 1e-12).  ON a multiple of 1000 the rounding of
-// the three double products decides between q and q-1; since 114*b mod 1000 has period 500 > 255, (r,g)
-// determines that b uniquely, so one bit per (r,g) -- tabulated on the host by evaluating the reference
-// expression itself -- says whether the result is q-1.
-__device__ __align__(16) uint32_t d_gray_down[2048];  // bit (r<<8|g): the double evaluation lands below q
-
+// the three double products decides between q and q-1: those pixels (0.1 %) evaluate the reference
+// expression itself in double on the device (rip_fused_x3.cuh, gray_down_mask).
 __device__ __forceinline__ float sqrt_approx(float x)
 {
     float y;
@@ -77,7 +74,7 @@ __device__ __forceinline__ float sqrt_approx(float x)
     return y;
 }
 
-#include "rip_fused_x2.cuh"
+#include "rip_fused_x3.cuh"
 
 }  // namespace
 
@@ -98,38 +95,52 @@ bool fused_supported(int W, int H, int fmt, int ksize, const uint8_t *d_in, cons
     return true;
 }
 
-// Guard band for the fast path, and the separable taps that minimise it.  See DESIGN.md
-// ("Exact blur at separable cost") for the derivation:
-//   |S_ref - S| <= u * 255 * (sum_i w_i (25 - i) + sum_i w_i)      (sequential fp32 sum, u = 2^-24)
-//   |S~    - S| <= 255 * sum|w_ij - g_i g_j|  +  9 u * 255 * sum_i w_i   (separable FMA evaluation)
+// half an ulp of the fp32 binade that holds x (x > 0): the largest rounding error of a result whose magnitude is <= x
+static double hulp(double x) { return x > 0.0 ? std::ldexp(1.0, (int)std::floor(std::log2(x)) - 24) : 0.0; }
+
+// Guard band for the fast path, and the separable taps that minimise it: a rigorous bound on |S~ - S_ref|, every rounding
+// bounded by half an ulp of the BINADE its result can reach (round 1 used u * |value|, up to twice as much; the band went
+// from 14 to 8 ulps of 2^-15 for the reference's weights, i.e. 40 % fewer guard-band pixels).  With gray values <= 255,
+// w_k the 25 weights in the reference's order, W_k = w_0 + .. + w_k, g the separable taps (floats) and G = g0 + 2 g1 + 2 g2:
+//   reference (GaussianBlur.cpp:236-258: acc_k = fl(acc_{k-1} + fl(p_k w_k)), acc_0 = fl(p_0 w_0)):
+//     |S_ref - S| <= sum_k hulp(255 w_k) + sum_{k>=1} hulp(255 W_k)
+//   separable model in exact arithmetic:        |S_sep - S| <= 255 sum_ij |w_ij - g_i g_j|
+//   fast path (rip_fused_x3.cuh): the vertical pass rounds three times (five in the accumulate form; the larger bound is
+//     used), |V - V_exact| <= E_V; the pair sums e = fl(V + V') once more, <= E_e = hulp(510 G); the horizontal chain
+//     fl(g0 V + bias), fl(g1 e1 + .), fl(g2 e2 + .) rounds on the 2^-16 grid of [256, 512): its last rounding is the +1/2
+//     ulp in the choice of `a` (launch_fused_x2_n), the two inner ones add 2 * 2^-16:
+//     |S~ - S_sep| <= G E_V + (g1 + g2) E_e + 2^-15
+// (all scalings by powers of two in the kernel are exact and keep every intermediate a normal float, checked below).
 static bool plan_weights_band(const float *w25, float g[3], double *band_out)
 {
     double sum = 0.0;
     for (int i = 0; i < 25; i++) {
         if (!(w25[i] >= 0.0f) || !std::isfinite(w25[i])) return false;
-        // the x2 kernel feeds gray in as q * 2^-149 and carries the 2^149 in the weights; a product must
-        // stay a normal float for its rounding to equal the reference's (rip_fused_x2.cuh)
+        // the kernel feeds gray in as q * 2^-149 and carries the 2^149 in the weights; a product must
+        // stay a normal float for its rounding to equal the reference's (rip_fused_x3.cuh)
         if (w25[i] != 0.0f && w25[i] < 8.470329472543003e-22f /* 2^-70 */) return false;
         sum += (double)w25[i];
     }
     if (!(sum > 0.0) || 255.0 * sum >= 255.9) return false;  // floor(S) must stay <= 255
     // symmetric separable fit from the diagonal: g_k = sqrt(w[k][k])
-    double gd[3];
-    for (int k = 0; k < 3; k++) gd[k] = std::sqrt((double)w25[(2 + k) * 5 + (2 + k)]);
-    for (int k = 0; k < 3; k++) g[k] = (float)gd[k];
+    for (int k = 0; k < 3; k++) g[k] = (float)std::sqrt((double)w25[(2 + k) * 5 + (2 + k)]);
+    const double g0 = g[0], g1 = g[1], g2 = g[2], G = g0 + 2 * g1 + 2 * g2;
     double dev = 0.0;
     for (int ky = -2; ky <= 2; ky++)
         for (int kx = -2; kx <= 2; kx++)
             dev += std::fabs((double)w25[(ky + 2) * 5 + (kx + 2)] - (double)g[std::abs(ky)] * (double)g[std::abs(kx)]);
-    // reference error: acc_k = fl(acc_{k-1} + fl(p_k w_k)); each add errs by <= u*|acc_k| and
-    // acc_k <= 255 * (w_0 + .. + w_k), so the adds contribute <= u * 255 * sum_i w_i * (25 - i);
-    // the 25 rounded products add <= u * 255 * sum(w).  Fast path: <= 9 u * 255 * sum(w).
-    const double u = std::ldexp(1.0, -24);
-    double cum = 0.0;
-    for (int i = 0; i < 25; i++) cum += (double)w25[i] * (25 - i);
-    // (the bias rides in the horizontal FMA chain: its two inner results are rounded on the 2^-16 grid of
-    // [256, 512), i.e. by <= 256 u each, instead of relative to S~: + 512 u)
-    const double band = 255.0 * dev + u * (255.0 * (cum + sum + 9.0 * sum) + 512.0) * 1.02 + 1e-6;
+    const double up = 1.0 + 1e-6;   // (bounds that sit just below a power of two are pushed into the next binade: safe side)
+    double b_ref = 0.0, cumw = 0.0;
+    for (int k = 0; k < 25; k++) {
+        cumw += (double)w25[k];
+        b_ref += hulp(255.0 * w25[k] * up);
+        if (k >= 1) b_ref += hulp(255.0 * cumw + 1e-3);   // (+1e-3: the computed partial sums carry their own errors)
+    }
+    const double e_v = hulp(255.0 * g2 * up) + hulp(255.0 * (g2 + g1) * up) + hulp(255.0 * (g2 + g1 + g0) * up) +
+                       hulp(255.0 * (g2 + 2 * g1 + g0) * up) + hulp(255.0 * G * up);
+    const double e_e = hulp(510.0 * G * up);
+    const double b_fast = G * e_v + (g1 + g2) * e_e + std::ldexp(1.0, -15);
+    const double band = (255.0 * dev + b_ref + b_fast) * 1.01 + 1e-7;
     if (band > 0.05) return false;  // weights are not (close to) a symmetric separable kernel
     *band_out = band;
     return true;
@@ -158,39 +169,22 @@ static int pick_seg_rows(int out_rows, int n_frames, int n_band_groups, int devi
 
 static unsigned long long *g_slow_counter = nullptr;  // set by rip_debug_slow_path_stats
 
-// d_gray_down, per device, filled once by evaluating the reference expression (Comparator.cpp:41)
-// in double on the host for the 16 774 (r,g,b) triples whose 299r+587g+114b is a multiple of 1000.
-static int ensure_gray_table(int device, cudaStream_t stream)
+// bit v of flat_dec: the reference's sum over a CONSTANT 5x5 window of gray value v (GaussianBlur.cpp:236-258: float
+// accumulator from 0.0f, ky-major / kx-minor, one rounded product and one rounded add per tap) truncates to one
+// below the nearest integer.  Evaluated with the reference's own sequence for the weights in use; the kernel's
+// flat-region shortcut reads it instead of replaying 25 taps per pixel.
+static void plan_flat_table(const float *w25, uint32_t flat_dec[8])
 {
-    static std::mutex mu;
-    static bool done[64];
-    if (device < 0 || device >= 64) return fail(RIP_EINVAL, "device %d out of range", device);
-    std::lock_guard<std::mutex> lock(mu);
-    if (done[device]) return RIP_OK;
-    static uint32_t bits[2048];
-    static bool built = false;
-    if (!built) {
-        memset(bits, 0, sizeof(bits));
-        for (int r = 0; r < 256; r++)
-            for (int g = 0; g < 256; g++)
-                for (int b = 0; b < 256; b++) {
-                    const int t = 299 * r + 587 * g + 114 * b;
-                    if (t % 1000) continue;
-                    volatile double s = 0.299 * r;  // volatile: no contraction, strict left-to-right doubles
-                    volatile double s2 = 0.587 * g;
-                    volatile double s3 = 0.114 * b;
-                    volatile double sum = s + s2;
-                    sum = sum + s3;
-                    if ((int)sum < t / 1000) bits[(r << 8 | g) >> 5] |= 1u << ((r << 8 | g) & 31);
-                }
-        built = true;
+    memset(flat_dec, 0, 8 * sizeof(uint32_t));
+    for (int v = 0; v < 256; v++) {
+        volatile float acc = 0.0f;   // volatile: every product and every add is rounded to float, none is fused
+        for (int i = 0; i < 25; i++) {
+            volatile float prod = (float)v * w25[i];
+            acc = acc + prod;
+        }
+        const float s = acc;
+        if (s < rintf(s)) flat_dec[v >> 5] |= 1u << (v & 31);
     }
-    // stream-ordered before the first kernel that reads the table (the library's streams are non-blocking, so a copy on
-    // the legacy stream would not be); the source is static storage, so a staged pageable copy is safe
-    RIP_CUDA(cudaMemcpyToSymbolAsync(d_gray_down, bits, sizeof(bits), 0, cudaMemcpyHostToDevice, stream));
-    RIP_CUDA(cudaStreamSynchronize(stream));   // once per device: later launches on OTHER streams must see it too
-    done[device] = true;
-    return RIP_OK;
 }
 
 // ---- x2 kernel (the default) --------------------------------------------------------------------
@@ -220,11 +214,15 @@ static int launch_fused_x2_n(cudaStream_t s, FusedParams p, int n_frames, int fm
         xp.gh0 = std::ldexp(g[0], 74); xp.gh1 = std::ldexp(g[1], 74); xp.gh2 = std::ldexp(g[2], 74);
         // S~ + 256 is rounded to a multiple of ulp = 2^-15 (error <= ulp/2).  A pixel whose 15 fraction
         // bits are >= a and <= 2^15 - 1 - a has frac(S~) in [(a - 1/2) ulp, 1 - (a + 1/2) ulp], i.e. S~ is
-        // >= band away from an integer when a >= band / ulp + 1/2; all others are replayed exactly.
+        // >= band away from an integer when a >= band / ulp + 1/2; all others are inside the guard band.
+        // The bias carries the +a ulps (exact: a multiple of the ulp), so "inside" is "fraction bits < 2a" and
+        // the masked value of such a pixel is the integer n it is close to; the reference's result is n or n - 1.
         const double ulp = std::ldexp(1.0, -kFracBits);
         const uint32_t a = (uint32_t)std::ceil(band / ulp + 0.5);
-        xp.zoff = a << (32 - kFracBits);
+        xp.bias = (float)(256.0 + a * ulp);
         xp.zthr = (2u * a) << (32 - kFracBits);
+        for (int i = 0; i < 25; i++) xp.ws[i] = std::ldexp(p.w[i], 100);   // (exact: w >= 2^-70 or 0, checked in plan_weights_band)
+        plan_flat_table(p.w, xp.flat_dec);
     }
     const long long blocks = (long long)n_frames * p.n_segs * p.n_band_groups;
     if (blocks <= 0 || blocks > 0x7fffffffLL) return fail(RIP_EINVAL, "rip_fused: grid of %lld blocks is out of range", blocks);
@@ -255,7 +253,6 @@ int launch_fused(cudaStream_t s, const uint8_t *d_in, uint8_t *d_out, int W, int
                  bool with_blur, const float *weights25, int in_row0, int in_rows, int out_row0, int out_rows,
                  int device)
 {
-    if (int rc = ensure_gray_table(device, s)) return rc;
     FusedParams p;
     memset(&p, 0, sizeof(p));
     p.in = d_in; p.out = d_out; p.W = W; p.H = H;
@@ -284,7 +281,7 @@ namespace {
 
 // the x2 kernel's versions of the same two shortcuts: (1) sqrt.approx, then a multiply by 2^-149 (or
 // 2^-127 on the 2^-22-scaled values of the no-blur variant) whose denormal result IS the rounded
-// integer, then I2IP.U8.S32.SAT; (2) IDP.2A + FMUL2.RM / FFMA2.RP gray with the cold (r,g) lookup.
+// integer, then I2IP.U8.S32.SAT; (2) IDP.2A + FMUL2.RM / FFMA2.RP gray with the cold double evaluation.
 __global__ void selftest_sqrt_x2_kernel(unsigned long long *bad)
 {
     const unsigned m2_max = 2u * 1020u * 1020u;
@@ -302,10 +299,6 @@ template <int NPX, int CN, bool BGR>
 __global__ void selftest_gray_x2_kernel(unsigned long long *bad)
 {
     constexpr int NP = NPX / 2, NW = NPX * CN / 4;
-    __shared__ uint32_t table[2048];
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) table[i] = d_gray_down[i];
-    __syncthreads();
-    const uint32_t table_s = (uint32_t)__cvta_generic_to_shared(table);
     // thread q handles triples NPX*q .. NPX*q + NPX-1 (triple i: c0 = i & 255, c1 = (i >> 8) & 255, c2 = i >> 16)
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < (1u << 24) / NPX; q += gridDim.x * blockDim.x) {
         uint8_t bytes[NW * 4];
@@ -321,7 +314,9 @@ __global__ void selftest_gray_x2_kernel(unsigned long long *bad)
             w[k] = bytes[4 * k] | (bytes[4 * k + 1] << 8) | (bytes[4 * k + 2] << 16) | ((uint32_t)bytes[4 * k + 3] << 24);
         u64 Q[NP], E[NP];
         const uint32_t any = gray_x2<NPX, CN, BGR>(w, Q, E);
-        if (any & 1u) gray_fix_x2<NPX, CN, BGR>(w, Q, E, table_s);
+        if (__any_sync(FULL, any & 1u)) {
+            if (any & 1u) gray_fix_x2<NPX, CN, BGR>(w, Q, E);
+        }
 #pragma unroll
         for (int j = 0; j < NPX; j++) {
             const unsigned i = NPX * q + j;
@@ -337,7 +332,6 @@ __global__ void selftest_gray_x2_kernel(unsigned long long *bad)
 
 int fused_selftest(int device, unsigned long long *checked, unsigned long long *mismatches)
 {
-    if (int rc = ensure_gray_table(device, nullptr)) return rc;
     unsigned long long *d_bad = nullptr;
     RIP_CUDA(cudaMalloc(&d_bad, sizeof(*d_bad)));
     RIP_CUDA(cudaMemset(d_bad, 0, sizeof(*d_bad)));
