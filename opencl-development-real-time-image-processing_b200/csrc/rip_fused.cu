@@ -221,8 +221,8 @@ static int launch_fused_x2_n(cudaStream_t s, FusedParams p, int n_frames, int fm
         const uint32_t a = (uint32_t)std::ceil(band / ulp + 0.5);
         xp.bias = (float)(256.0 + a * ulp);
         xp.zthr = (2u * a) << (32 - kFracBits);
-        for (int i = 0; i < 25; i++) xp.ws[i] = std::ldexp(p.w[i], 100);   // (exact: w >= 2^-70 or 0, checked in plan_weights_band)
-        plan_flat_table(p.w, xp.flat_dec);
+        for (int i = 0; i < 25; i++) xp.fix.ws[i] = std::ldexp(p.w[i], 100);   // (exact: w >= 2^-70 or 0, checked in plan_weights_band)
+        plan_flat_table(p.w, xp.fix.flat_dec);
     }
     const long long blocks = (long long)n_frames * p.n_segs * p.n_band_groups;
     if (blocks <= 0 || blocks > 0x7fffffffLL) return fail(RIP_EINVAL, "rip_fused: grid of %lld blocks is out of range", blocks);

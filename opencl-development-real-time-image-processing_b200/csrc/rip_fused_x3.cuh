@@ -77,14 +77,19 @@ constexpr float kBias = 256.0f;                      // [256, 512): ulp 2^-15, f
 constexpr uint32_t kBiasMask = 0xffff8000u;
 constexpr int kFracBits = 15;
 
+// what the out-of-line blur fix reads (it gets a pointer to this part of the kernel parameters)
+struct BlurFixConst {
+    float ws[25];          // the exact 2-D weights times 2^100 (for the replay: products stay normal, see blur_replay_lane)
+    uint32_t flat_dec[8];  // bit v: a constant 5x5 window of gray v gives the reference sum S with trunc(S) = rint(S) - 1
+};
+
 struct X2Params {
     FusedParams f;
     float gv0, gv1, gv2;   // vertical taps   * 2^75  (gray enters as the integer bit pattern q = q * 2^-149)
     float gh0, gh1, gh2;   // horizontal taps * 2^74
     float bias;            // kBias + a * 2^-15: the guard band's lower edge rides in the bias, so that
     uint32_t zthr;         // a pixel is inside the band iff (bits << 17) < zthr = 2a << 17, and its masked value is then n
-    float ws[25];          // the exact 2-D weights times 2^100 (for the replay: products stay normal, see blur_fix_lane)
-    uint32_t flat_dec[8];  // bit v: a constant 5x5 window of gray v gives the reference sum S with trunc(S) = rint(S) - 1
+    BlurFixConst fix;
 };
 
 // ---- exact gray of NPX packed pixels -> NPX/2 pairs of integer bit patterns ---------------------
@@ -158,60 +163,60 @@ __device__ __forceinline__ uint32_t ring_off(uint32_t c)
     return (pr / 2u) * 512u + L * 16u + (pr % 2u) * 8u + h * 4u;
 }
 
-// flagged-pixel mask of a lane from the E pairs of gray_x2 (bit j = pixel j).  Every half of E is 1
-// (flagged), +0 or -0, so a shift-add chain collects the bits (the sign bit of a -0 either leaves the
-// word or lands in bit 31, which the final mask drops).
-template <int NPX>
-__device__ __forceinline__ uint32_t gray_flag_mask(const u64 *E)
-{
-    constexpr int NP = NPX / 2;
-    uint32_t m = 0;
-#pragma unroll
-    for (int j = 0; j < NP; j++) m += (lo2u(E[j]) << j) + (hi2u(E[j]) << (j + NP));
-    return m & ((1u << NPX) - 1u);
-}
+// ---- cold, lane-parallel: the exact gray of pixels whose t = 299r+587g+114b is a multiple of 1000 -----------------------------
+// c_gray_down: bit (r | g << 8) = "the reference's double expression (Comparator.cpp:41) lands one below t/1000" for the one b
+// that makes t a multiple of 1000 with this (r, g) (tools/make_gray_table.py evaluates the reference expression itself; the
+// device self-test checks all 2^24 triples against a double evaluation).  An initialised __constant__ array: part of the module
+// image, nothing to copy or order at run time.
+__constant__ uint32_t c_gray_down[2048] = {
+#include "rip_gray_table.inc"
+};
 
-// the reference's gray expression, Comparator.cpp:41: (uchar)(0.299*r + 0.587*g + 0.114*b) in double, left to right,
-// unfused; returns 1 iff it truncates to one below t/1000 (only asked for t = 299r+587g+114b = 1000 q).  (A bit table
-// per (r, g) was measured in constant memory, in global memory behind L1 and behind L1 with evict_last / no_allocate
-// hints: 430-436 us per 32 4K frames each, against 429 us for this evaluation -- the cost of the cold path is the
-// excursion itself, not the lookup; profiles/README.md.)
-__device__ __forceinline__ uint32_t gray_lands_below(uint32_t r, uint32_t g, uint32_t b)
+// bit 0 of the result: table bit of pixel j of the lane (bytes of the pixel at compile-time positions of the raw words)
+template <int CN, bool BGR>
+__device__ __forceinline__ uint32_t gray_down_bit(const uint32_t *w, int j)
 {
-    const double s = __dadd_rn(__dadd_rn(__dmul_rn(0.299, (double)r), __dmul_rn(0.587, (double)g)), __dmul_rn(0.114, (double)b));
-    const uint32_t t = 299u * r + 587u * g + 114u * b;
-    return s < (double)(t / 1000u) ? 1u : 0u;
-}
-
-// Cold, lane-parallel: which of the lane's pixels whose t = 299r+587g+114b is a multiple of 1000 (E from gray_x2) must
-// come out one below t/1000?  Decided by evaluating the reference expression itself in double (B200 has the FP64 rate
-// for a path that 0.1 % of the pixels take; no table, no shared memory for one, nothing to initialise).
-//   (1) all of the lane's pixels are the same colour (constant regions; every grey / white / clipped pixel has
-//       t = 1000 v): one evaluation for the lane;  (2) otherwise one per flagged pixel, the channel bytes fetched with a
-//       run-time pixel index from a shared-memory copy of the lane's input (`raw`): no register select chains.
-template <int NPX, int CN, bool BGR>
-__device__ __forceinline__ uint32_t gray_down_mask(const uint32_t *w, const u64 *E, uint32_t raw)
-{
-    constexpr int NW = NPX * CN / 4;
-    uint32_t same = 0;
-#pragma unroll
-    for (int k = 1; k < NW; k++) same |= w[k] ^ w[0];
-    if (CN == 3) same |= w[0] ^ __byte_perm(w[0], 0u, 0x2103);   // 3-byte pixels: equal words are equal pixels only if r = g = b
-    // (one copy of the evaluation serves both cases: a constant lane evaluates its pixel 0 and replicates the answer)
-#pragma unroll
-    for (int k = 0; k + 1 < NW; k += 2) sts_b64(raw + 4 * k, pk2u(w[k], w[k + 1]));
-    if (NW & 1) sts_u32(raw + 4 * (NW - 1), w[NW - 1]);
-    uint32_t m = same == 0u ? 1u : gray_flag_mask<NPX>(E), down = 0;
-#pragma unroll 1
-    while (m) {
-        const uint32_t j = (uint32_t)__ffs(m) - 1u;
-        m &= m - 1;
-        const uint32_t a = raw + CN * j;
-        const uint32_t c0 = lds_u8(a), c1 = lds_u8(a + 1), c2 = lds_u8(a + 2);
-        down |= gray_lands_below(BGR ? c2 : c0, c1, BGR ? c0 : c2) << j;
+    const int o = CN * j + (BGR ? 1 : 0), a = o / 4, s = o % 4;   // the key's two bytes start at byte o of the lane's raw bytes: (r, g) or, for BGR, (g, r)
+    uint32_t key;   // r | g << 8 in the low 16 bits, anything above
+    if (!BGR) {
+        key = s == 0 ? w[a] : s <= 2 ? w[a] >> (8 * s) : __funnelshift_r(w[a], w[a + 1], 24);
+    } else {        // bytes (g, r) -> (r, g)
+        key = s <= 2 ? __byte_perm(w[a], 0u, (uint32_t)((s + 1) | (s << 4))) : __byte_perm(w[a], w[a + 1], 0x34u);
     }
-    if (same == 0u) down = down ? (1u << NPX) - 1u : 0u;   // (the caller only asks when the pixels are flagged)
-    return down;
+    const uint32_t word = c_gray_down[(key >> 5) & 2047u];
+    return word >> (key & 31u);
+}
+
+// Every half of E (gray_x2) is 1 (t is a multiple of 1000), +0 or -0.  Pair by pair: where a half is flagged, subtract the table
+// bit of that pixel.  Everything sits at compile-time positions: no pixel index at run time, no staging in shared memory, no
+// loop -- one flagged pixel costs the four pair tests and one 14-instruction block (round 2's first version staged the raw
+// bytes in shared memory, looped over a bit mask and evaluated the double expression: ~95 warp instructions per excursion,
+// and an excursion costs its instruction count times the ~6 cycles between two issues of one warp).
+template <int NPX, int CN, bool BGR>
+__device__ __forceinline__ void gray_fix_pairs(const uint32_t *w, u64 *Q, const u64 *E)
+{
+    constexpr int NP = NPX / 2, NW = NPX * CN / 4;
+    // constant regions first (every grey / white / clipped pixel has t = 1000 v, so flat content enters here on every row):
+    // all raw words equal -- and r = g = b for 3-byte pixels -- means one colour, one table bit for the lane
+    uint32_t diff = 0;
+#pragma unroll
+    for (int k = 1; k < NW; k++) diff |= w[k] ^ w[0];
+    if (CN == 3) diff |= w[0] ^ __byte_perm(w[0], 0u, 0x2103);
+    if (diff == 0u) {
+        const uint32_t sub = gray_down_bit<CN, BGR>(w, 0) & lo2u(E[0]) & 1u;
+#pragma unroll
+        for (int k = 0; k < NP; k++) Q[k] = pk2u(lo2u(Q[k]) - sub, hi2u(Q[k]) - sub);
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        const uint32_t el = lo2u(E[k]), eh = hi2u(E[k]);
+        if ((el | eh) & 1u) {
+            const uint32_t ql = lo2u(Q[k]) - (gray_down_bit<CN, BGR>(w, k) & el & 1u);
+            const uint32_t qh = hi2u(Q[k]) - (gray_down_bit<CN, BGR>(w, k + NP) & eh & 1u);
+            Q[k] = pk2u(ql, qh);
+        }
+    }
 }
 
 // in place: pixel j of the lane -= bit j of `dec`, on integer bit patterns (gray) or, scaled by 2^15, on the biased
@@ -228,14 +233,11 @@ __device__ __forceinline__ void apply_dec(u64 *V, uint32_t dec)
     }
 }
 
-// register-in / register-out gray fix for the self-test (not used by the kernel)
+// register-in / register-out gray fix for the self-test
 template <int NPX, int CN, bool BGR>
 __device__ __forceinline__ void gray_fix_x2(const uint32_t *w, u64 *Q, const u64 *E)
 {
-    constexpr int NWP = (NPX * CN / 4 + 1) & ~1;
-    __shared__ __align__(16) uint32_t scratch[256 * NWP];
-    const uint32_t raw = (uint32_t)__cvta_generic_to_shared(scratch + threadIdx.x * NWP);
-    apply_dec<NPX, 0>(Q, gray_down_mask<NPX, CN, BGR>(w, E, raw) & gray_flag_mask<NPX>(E));
+    gray_fix_pairs<NPX, CN, BGR>(w, Q, E);
 }
 
 template <int NPX, int CN>
@@ -292,7 +294,6 @@ struct GeoX {
     uint32_t ring_lane;      // shared-memory byte address of this lane's 16 bytes in plane 0 of slot 0 of the warp's gray ring
     uint32_t ringA, ringB;   // main loop: ring_lane + the half (slots 0-2 / 3-5) this trip writes / wrote last trip
     uint32_t slot;           // head / tail rows: slot of the newest gray row
-    uint32_t raw;            // byte address of this lane's scratch copy of its input bytes (gray fix)
     uint32_t in_pitch;
     int adv_lo, adv_n;       // the source pointer advances before the load of step r iff 0 <= r - adv_lo < adv_n
     uint32_t pf_off;         // byte offset from src of the line this lane prefetches into L2 (0: none)
@@ -302,6 +303,7 @@ struct GeoX {
     uint32_t need;           // pixels of this lane whose blurred value feeds an output (bit j = pixel j): all of lanes 1..30,
                              // only the pixel next to the band in the two halo lanes, none in lanes outside the image
     bool e_left, e_right;    // this lane holds image column 0 / W-1 (border rules in x apply to it)
+    bool edge_warp;          // warp-uniform: some lane of this warp has e_left or e_right set (2 of the 16 bands of a 4K row)
     uint32_t store_lane;
     int r_store, r_last;     // first / last step that produces an output row
 };
@@ -317,7 +319,7 @@ struct GeoX {
 // 5x5 window of the lane is that constant and the answer is bit v of xp.flat_dec, which the host evaluated with the
 // reference's own sequence for the weights in use.  Returns 0 / 1 = the answer, 2 = the neighbourhood is not constant.
 template <int NPX>
-__device__ RIP_REPLAY_FN uint32_t blur_flat_lane(uint32_t ring0, uint32_t newest, uint32_t lane_cols, const X2Params &xp)
+__device__ RIP_REPLAY_FN uint32_t blur_flat_lane(uint32_t ring0, uint32_t newest, uint32_t lane_cols, const uint32_t *flat_dec)
 {
     constexpr uint32_t kRowB = 32 * NPX * 4;
     const int lane = (int)(lane_cols & 31u), cmin = (int)((lane_cols >> 5) & 0x3ffu), cmax = (int)(lane_cols >> 15);
@@ -341,7 +343,7 @@ __device__ RIP_REPLAY_FN uint32_t blur_flat_lane(uint32_t ring0, uint32_t newest
         diff |= (lds_u32(row + or0) ^ v) | (lds_u32(row + or1) ^ v);
         row = row == ring0 ? ring0 + ((uint32_t)kRing - 1u) * kRowB : row - kRowB;
     }
-    return diff ? 2u : (xp.flat_dec[v >> 5] >> (v & 31u)) & 1u;
+    return diff ? 2u : (flat_dec[v >> 5] >> (v & 31u)) & 1u;
 }
 
 // byte offset, relative to the lane's own 16 bytes in plane 0, of the ring word of the pixel `rel - 2` columns from
@@ -364,45 +366,43 @@ __constant__ RingRel<8> c_ring_rel8;
 __constant__ RingRel<4> c_ring_rel4;
 
 // (2) the reference's 25-tap sequence for each of the pixels in `my` (bit j = pixel j); returns the mask of those whose
-// result is n - 1.  The ring holds gray as integer bit patterns (= q * 2^-149 as floats) and xp.ws the weights times
+// result is n - 1.  The ring holds gray as integer bit patterns (= q * 2^-149 as floats) and ws the weights times
 // 2^100: fl(q*2^-149 * w*2^100) = fl(q * w) * 2^-49 exactly (same mantissa, results stay normal), likewise every partial
 // sum, so the scaled chain rounds exactly like the reference's (ky-major / kx-minor from 0.0f, unfused) and needs no
-// integer-to-float conversion.  Columns are clamped to [cmin, cmax] (clamp-to-edge, GaussianBlur.cpp:240).
+// integer-to-float conversion.  `rowaddr[i]` = shared-memory address of this lane's 16 bytes (plane 0) of gray row r - i;
+// in the main loop those are compile-time offsets from two registers, so the 25 loads need ten address adds.  Columns
+// are clamped to the image (clamp-to-edge, GaussianBlur.cpp:240) only in the two lanes that hold column 0 / W-1.
+// What an excursion costs is its executed instruction count (the kernel's time is its warp-instruction count at a steady
+// ~65 % issue rate, profiles/README.md), so everything that is not the 25 loads, 25 products and 25 adds is kept short.
+// (Out of line -- one __noinline__ copy for all row bodies, main loop 1126 instead of 1693 instructions -- was measured:
+// 445 us against 431 us; the call sequence and the run-time ring slots cost more than the smaller loop gains.)
 template <int NPX>
-__device__ RIP_REPLAY_FN uint32_t blur_replay_lane(uint32_t my, uint32_t ring0, uint32_t newest, uint32_t lane_cols, const X2Params &xp)
+__device__ RIP_REPLAY_FN uint32_t blur_replay_lane(uint32_t my, const uint32_t (&rowaddr)[5], bool edge_lane, uint32_t lane_cols, const BlurFixConst &cst)
 {
-    constexpr uint32_t kRowB = 32 * NPX * 4;
-    const int lane = (int)(lane_cols & 31u), cmin = (int)((lane_cols >> 5) & 0x3ffu), cmax = (int)(lane_cols >> 15);
-    const int rel_lo = cmin - NPX * lane + 2, rel_hi = cmax - NPX * lane + 2;   // clamp-to-edge in lane-relative columns
     const int *lut = NPX == 8 ? c_ring_rel8.v : c_ring_rel4.v;
-    uint32_t oldest = newest + (uint32_t)kRing - 4u;   // slot of row r-4
-    oldest = oldest >= (uint32_t)kRing ? oldest - (uint32_t)kRing : oldest;
-    const uint32_t base = ring0 + 16u * (uint32_t)lane;
     uint32_t dec = 0;
 #pragma unroll 1
     while (my) {
         const uint32_t j = (uint32_t)__ffs(my) - 1u;
         my &= my - 1u;
         uint32_t off[5];
+        if (edge_lane) {
+            const int lane = (int)(lane_cols & 31u), cmin = (int)((lane_cols >> 5) & 0x3ffu), cmax = (int)(lane_cols >> 15);
+            const int rel_lo = cmin - NPX * lane + 2, rel_hi = cmax - NPX * lane + 2;   // clamp-to-edge in lane-relative columns
 #pragma unroll
-        for (int kx = 0; kx < 5; kx++) off[kx] = base + (uint32_t)lut[min(max((int)j + kx, rel_lo), rel_hi)];
-        // (unrolled: what a cold excursion costs is its LATENCY -- the warp makes no other progress meanwhile -- and a
-        // rolled loop pays the shared-memory round trip once per window row: 433 -> see profiles/README.md)
-        uint32_t rowb[5];
-        uint32_t s = oldest;
+            for (int kx = 0; kx < 5; kx++) off[kx] = (uint32_t)lut[min(max((int)j + kx, rel_lo), rel_hi)];
+        } else {
 #pragma unroll
-        for (int ky = 0; ky < 5; ky++) {
-            rowb[ky] = s * kRowB;
-            s = s == (uint32_t)kRing - 1u ? 0u : s + 1u;
+            for (int kx = 0; kx < 5; kx++) off[kx] = (uint32_t)lut[j + kx];
         }
         float g25[25];
 #pragma unroll
         for (int ky = 0; ky < 5; ky++)
 #pragma unroll
-            for (int kx = 0; kx < 5; kx++) g25[ky * 5 + kx] = __uint_as_float(lds_u32(rowb[ky] + off[kx]));
+            for (int kx = 0; kx < 5; kx++) g25[ky * 5 + kx] = __uint_as_float(lds_u32(rowaddr[4 - ky] + off[kx]));
         float acc = 0.f;
 #pragma unroll
-        for (int t = 0; t < 25; t++) acc = __fadd_rn(acc, __fmul_rn(g25[t], xp.ws[t]));
+        for (int t = 0; t < 25; t++) acc = __fadd_rn(acc, __fmul_rn(g25[t], cst.ws[t]));
         acc = __fmul_rn(acc, 562949953421312.0f);   // * 2^49: back to the reference's scale (exact)
         dec |= (acc < rintf(acc) ? 1u : 0u) << j;
     }
@@ -437,13 +437,16 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
         u64 E[NP];
         const uint32_t flagged = gray_x2<NPX, CN, BGR>(buf.w, Q, E) & 1u;
 #if !defined(RIP_X2_NOCOLD) && !defined(RIP_X3_NOGRAYCOLD)   // (experiment switches: hot path only, wrong results)
+#ifdef RIP_X3_NEVERCOLD   // (experiment: the cold code is present but never runs -- what does its mere presence cost?)
+        if (CN != 1 && __builtin_expect(__any_sync(FULL, flagged && xp.zthr == 0xdeadbeefu), 0)) {
+#else
         if (CN != 1 && __builtin_expect(__any_sync(FULL, flagged), 0)) {
+#endif
             if (flagged) {
 #ifdef RIP_X3_EMPTYCOLD   // (experiment: the branches without their work -- what does the control structure alone cost?)
                 asm volatile("" : "+l"(Q[0]));
 #else
-                const uint32_t down = gray_down_mask<NPX, CN, BGR>(buf.w, E, geo.raw);
-                if (down) apply_dec<NPX, 0>(Q, down);
+                gray_fix_pairs<NPX, CN, BGR>(buf.w, Q, E);
 #endif
             }
         }
@@ -533,7 +536,7 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
         // clamp applies to V: left of column 0 / right of column W-1 repeat it.
         float Vm2 = __shfl_up_sync(FULL, hi2(V[NP - 2]), 1), Vm1 = __shfl_up_sync(FULL, hi2(V[NP - 1]), 1);
         float Vp0 = __shfl_down_sync(FULL, lo2(V[0]), 1), Vp1 = __shfl_down_sync(FULL, lo2(V[1]), 1);
-        if constexpr (EDGE) {
+        if (EDGE && geo.edge_warp) {   // (interior bands skip the selects where ptxas keeps the branch)
             Vm2 = geo.e_left ? lo2(V[0]) : Vm2;
             Vm1 = geo.e_left ? lo2(V[0]) : Vm1;
             Vp0 = geo.e_right ? hi2(V[NP - 1]) : Vp0;
@@ -568,36 +571,46 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
             zmin = __vimin3_u32(zmin, lo2u(F[j]) << (32 - kFracBits), hi2u(F[j]) << (32 - kFracBits));
         const uint32_t flagged = zmin < xp.zthr ? 1u : 0u;
 #if !defined(RIP_X2_NOCOLD) && !defined(RIP_X3_NOBLURCOLD)
+#ifdef RIP_X3_NEVERCOLD
+        if (__builtin_expect(__any_sync(FULL, flagged && xp.bias == 12345.0f), 0)) {
+#else
         if (__builtin_expect(__any_sync(FULL, flagged), 0)) {
+#endif
             __syncwarp();  // the newest ring row was just stored by the other lanes
 #ifdef RIP_X3_EMPTYCOLD
             if (flagged) asm volatile("" : "+l"(F[0]));
 #else
             if (flagged) {
-                const uint32_t ring0 = geo.ring_lane - 16u * (uint32_t)geo.lane, newest = (rowaddr[0] - geo.ring_lane) / kRowB;
-                uint32_t my = geo.need, dec = 2u;
-                // constant regions first: the fast path's values of the lane are then bit-identical (a cheap necessary
-                // condition), every pixel is inside the band, and one table bit answers for all of them
-                uint32_t same = 0;
+                // which pixels are inside the band ... and feed an output
+                uint32_t my = 0;
 #pragma unroll
-                for (int j = 0; j < NP; j++) same |= (lo2u(F[j]) ^ lo2u(F[0])) | (hi2u(F[j]) ^ lo2u(F[0]));
-                if (same == 0u) dec = blur_flat_lane<NPX>(ring0, newest, geo.lane_cols, xp);
-                if (dec == 2u) {   // the general case: which pixels are inside the band, then the reference's sequence for each
-                    my = 0;
+                for (int j = 0; j < NP; j++) {
+                    my |= ((lo2u(F[j]) << (32 - kFracBits)) < xp.zthr ? 1u : 0u) << j;
+                    my |= ((hi2u(F[j]) << (32 - kFracBits)) < xp.zthr ? 1u : 0u) << (j + NP);
+                }
+                my &= geo.need;
+                if (my) {
+                    uint32_t dec = 2u;
+                    // constant regions: every pixel of the lane is inside the band and the fast path's values are bit-identical
+                    // (a cheap necessary condition); then one table bit answers for all of them.  A lane-divergent branch that
+                    // textured content does not take.
+                    if (my == (1u << NPX) - 1u) {
+                        uint32_t same = 0;
 #pragma unroll
-                    for (int j = 0; j < NP; j++) {
-                        my |= ((lo2u(F[j]) << (32 - kFracBits)) < xp.zthr ? 1u : 0u) << j;
-                        my |= ((hi2u(F[j]) << (32 - kFracBits)) < xp.zthr ? 1u : 0u) << (j + NP);
+                        for (int j = 0; j < NP; j++) same |= (lo2u(F[j]) ^ lo2u(F[0])) | (hi2u(F[j]) ^ lo2u(F[0]));
+                        if (same == 0u) {
+                            const uint32_t ring0 = geo.ring_lane - 16u * (uint32_t)geo.lane, newest = (rowaddr[0] - geo.ring_lane) / kRowB;
+                            dec = blur_flat_lane<NPX>(ring0, newest, geo.lane_cols, xp.fix.flat_dec);
+                            if (dec == 1u) dec = my;
+                        }
                     }
-                    my &= geo.need;    // ... that feed an output
-                    dec = my ? blur_replay_lane<NPX>(my, ring0, newest, geo.lane_cols, xp) : 0u;
-                } else {
-                    dec = dec ? my : 0u;
+                    // the general case: the reference's sequence for each pixel inside the band
+                    if (dec == 2u) dec = blur_replay_lane<NPX>(my, rowaddr, geo.e_left || geo.e_right, geo.lane_cols, xp.fix);
+                    if constexpr (STATS) {
+                        if (p.slow_counter) atomicAdd(p.slow_counter, (unsigned long long)__popc(my));
+                    }
+                    if (dec) apply_dec<NPX, kFracBits>(F, dec);   // 256 + n + fraction -> 256 + (n - 1) + fraction
                 }
-                if constexpr (STATS) {
-                    if (p.slow_counter && my) atomicAdd(p.slow_counter, (unsigned long long)__popc(my));
-                }
-                if (dec) apply_dec<NPX, kFracBits>(F, dec);   // 256 + n + fraction -> 256 + (n - 1) + fraction
             }
 #endif
             __syncwarp();  // every lane is done with the ring before the next step overwrites its oldest slot
@@ -638,7 +651,7 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
     // horizontal pass, BORDER_REFLECT_101 in x: gx = Vs[x+1] - Vs[x-1],  gy = Vd[x-1] + 2 Vd[x] + Vd[x+1]
     float sl = __shfl_up_sync(FULL, hi2(Vs[NP - 1]), 1), sr = __shfl_down_sync(FULL, lo2(Vs[0]), 1);
     float dl = __shfl_up_sync(FULL, hi2(Vd[NP - 1]), 1), dr = __shfl_down_sync(FULL, lo2(Vd[0]), 1);
-    if constexpr (EDGE) {
+    if (EDGE && geo.edge_warp) {
         sl = geo.e_left ? lo2(Vs[1]) : sl;             // x = -1 -> x = 1
         dl = geo.e_left ? lo2(Vd[1]) : dl;
         sr = geo.e_right ? hi2(Vs[NP - 2]) : sr;       // x = W  -> x = W-2
@@ -760,8 +773,6 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     const FusedParams &p = xp.f;
 
     __shared__ __align__(16) uint32_t ring[BLUR ? kWarpsPerBlock * kRing * kRowW : 4];
-    constexpr int NWP = (NW + 1) & ~1;   // (an even number of words per lane: the copy is written with 64-bit stores)
-    __shared__ __align__(16) uint32_t rawcopy[CN != 1 ? kWarpsPerBlock * 32 * NWP : 4];   // per lane: its input bytes of one row (gray fix)
     // no block-level barrier: the warps are independent from the first instruction on
 
     GeoX geo;
@@ -770,7 +781,10 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     geo.ring_lane = (uint32_t)__cvta_generic_to_shared(ring + (BLUR ? warp * kRing * kRowW : 0)) + 16u * (uint32_t)geo.lane;
     geo.ringA = geo.ringB = geo.ring_lane;
     geo.slot = 1u;   // seven head rows later the newest row sits in slot 2
-    geo.raw = (uint32_t)__cvta_generic_to_shared(rawcopy + (CN != 1 ? threadIdx.x * NWP : 0));
+    // A block is kWarpsPerBlock adjacent bands of one row segment.  (One band x four consecutive segments per block -- the band,
+    // and with it "does this warp touch an image border", block-uniform -- was measured in round 2: the loop bounds then depend
+    // on the warp, ptxas guards every shuffle with BRA.DIV, 733 instead of 647 hot instructions per trip; one-warp blocks, where
+    // everything is uniform: 449 us against 431 us.)
     int bid = blockIdx.x;
     const int bg = bid % p.n_band_groups; bid /= p.n_band_groups;
     const int seg = bid % p.n_segs;
@@ -785,6 +799,7 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     const int lane_last = (W - xw0) / NPX;         // lane holding the last NPX pixels of the row (may be > 31)
     geo.e_left = (band == 0) && geo.lane == 1;
     geo.e_right = geo.lane == lane_last;
+    geo.edge_warp = band == 0 || lane_last <= 31;
     geo.lane_cols = (uint32_t)geo.lane | (uint32_t)(band == 0 ? NPX : 0) << 5 | (uint32_t)(min(lane_last, 31) * NPX + NPX - 1) << 15;
     geo.need = !in_img ? 0u : geo.lane == 0 ? 1u << (NPX - 1) : geo.lane == 31 ? 1u : (1u << NPX) - 1u;
     const int ys = p.out_row0 + seg * p.seg_rows;
