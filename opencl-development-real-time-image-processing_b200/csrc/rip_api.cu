@@ -51,7 +51,7 @@ static Options g_options;
 static std::once_flag g_options_once;
 static const struct { const char *name; int Options::*field; } kOptionTable[] = {
     {"RIP_DISABLE_FUSED", &Options::disable_fused}, {"RIP_FUSED_SEG", &Options::fused_seg}, {"RIP_FUSED_NPX", &Options::fused_npx},
-    {"RIP_FUSED_GENERIC", &Options::fused_generic}, {"RIP_BLUR_EXACT", &Options::blur_exact}, {"RIP_BLUR_TILED", &Options::blur_tiled},
+    {"RIP_FUSED_GENERIC", &Options::fused_generic}, {"RIP_FUSED_STAGED", &Options::fused_staged}, {"RIP_BLUR_EXACT", &Options::blur_exact}, {"RIP_BLUR_TILED", &Options::blur_tiled},
     {"RIP_BLUR_STREAM", &Options::blur_stream},
 };
 
@@ -707,9 +707,12 @@ extern "C" int rip_fused(int device, rip_stream stream, const uint8_t *d_in, uin
     cudaStream_t s = (cudaStream_t)stream;
     {
         float g3[3], thr;  // single-kernel path: 5x5, aligned shape, and weights the guard band can cover
-        if (ksize == 5 && fused_supported(width, height, in_format, 5, d_in, d_out) && fused_plan_weights(wts.w, g3, &thr))
+        if (ksize == 5 && !options().fused_generic && fused_supported(width, height, in_format, 5, d_in, d_out) && fused_plan_weights(wts.w, g3, &thr))
             return launch_fused(s, d_in, d_out, width, height, n_frames, in_format, true, wts.w, in_row0, in_rows, out_row0, out_rows, device);
     }
+    // every other shape, kernel size and weight set: still one kernel (no workspace), the reference's arithmetic throughout
+    if (!options().fused_staged)
+        return launch_fused_tile(s, d_in, d_out, width, height, n_frames, in_format, ksize, wts, in_row0, in_rows, out_row0, out_rows);
 
     // staged path: gray band -> exact KxK blur -> Sobel, through the caller's workspace
     size_t need = 0;

@@ -32,4 +32,8 @@ int launch_fused(cudaStream_t s, const uint8_t *d_in, uint8_t *d_out, int W, int
                  bool with_blur, const float *weights25, int in_row0, int in_rows, int out_row0, int out_rows,
                  int device);
 
+// rip_fused_tile.cu -- the same pipeline in one kernel for any shape, any odd K <= RIP_MAX_KSIZE, any weights (reference order throughout)
+int launch_fused_tile(cudaStream_t s, const uint8_t *d_in, uint8_t *d_out, int W, int H, int n_frames, int fmt, int ksize,
+                      const Weights &wts, int in_row0, int in_rows, int out_row0, int out_rows);
+
 }  // namespace rip

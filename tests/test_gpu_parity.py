@@ -271,18 +271,73 @@ def test_fused_formats_and_sigmas(ctx, oracle, fmt, cn, order, sigma, npx, opt):
     _eq(ctx.process(img, rip.OP_FUSED, fmt, ksize=5, weights=w), want, f"fused {order}{cn} sigma {sigma}")
 
 
-@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (5, 5), (75, 75), (33, 241), (40, 683)])
-def test_fused_staged_path_for_odd_shapes(ctx, oracle, shape):
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (5, 5), (75, 75), (33, 241), (40, 683), (2, 2), (17, 33), (16, 32), (49, 97)])
+@pytest.mark.parametrize("staged", [0, 1])
+def test_fused_odd_shapes_tile_kernel_and_staged_path(ctx, oracle, shape, staged, opt):
+    """Shapes the streaming kernel rejects: one any-shape tile kernel (rip_fused_tile.cu); round 1's three-kernel path stays
+    reachable behind a switch and must agree."""
+    opt("RIP_FUSED_STAGED", staged)
     img = synth_frame("uniform", shape[0], shape[1], 51)
     w = rip.gauss_weights(5, 1.0)
-    _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w), f"fused staged {shape}")
+    before = rip.launch_count()
+    _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w), f"fused odd shape {shape}")
+    streaming = shape[1] % 4 == 0 and shape[0] >= 2   # (the streaming kernel takes this one: one launch either way)
+    assert rip.launch_count() - before == (3 if staged and not streaming else 1)
 
 
-@pytest.mark.parametrize("k,sigma", [(3, 0.8), (7, 2.0), (17, 6.0)])
+def test_fused_reference_image_sizes_run_one_kernel(ctx, oracle, golden_images):
+    """The reference's own JPEGs (75, 160, 240, 640, 683 wide -- /root/reference/images, decoded pixels in tests/golden):
+    gray -> 5x5 -> Sobel is ONE launch on every one of them, whatever the width."""
+    w = rip.gauss_weights(5, 1.0)
+    for name, bgr in golden_images.items():
+        if not name.endswith(".bgr"):
+            continue
+        before = rip.launch_count()
+        got = ctx.process(np.ascontiguousarray(bgr), rip.OP_FUSED, rip.FMT_BGR8, ksize=5, weights=w)
+        assert rip.launch_count() - before == 1, name
+        _eq(got, oracle.fused(np.ascontiguousarray(bgr[..., ::-1]), 5, weights=w, threads=0), f"fused {name} {bgr.shape}")
+
+
+@pytest.mark.parametrize("fmt,cn", [(rip.FMT_RGB8, 3), (rip.FMT_BGR8, 3), (rip.FMT_RGBA8, 4), (rip.FMT_BGRA8, 4), (rip.FMT_GRAY8, 1)])
+def test_fused_tile_kernel_formats_batches_bands(ctx, oracle, fmt, cn, opt):
+    """The tile kernel forced on a shape the streaming kernel would take: every format, a batch, row bands."""
+    opt("RIP_FUSED_GENERIC", 1)
+    h, wd, n = 61, 136, 3
+    w = rip.gauss_weights(5, 1.5)
+    rgb = [synth_frame("uniform" if i else "smooth", h, wd, 400 + i) for i in range(n)]
+    if cn == 1:
+        frames = np.stack([oracle.gray(f) for f in rgb])
+        want = [oracle.sobel(oracle.blur(g, 5, weights=w)) for g in frames]
+    else:
+        order = slice(None, None, -1) if fmt in (rip.FMT_BGR8, rip.FMT_BGRA8) else slice(None)
+        frames = np.stack([np.ascontiguousarray(f[..., order]) for f in rgb])
+        if cn == 4:
+            frames = np.ascontiguousarray(np.concatenate([frames, np.full(frames.shape[:3] + (1,), 200, np.uint8)], -1))
+        want = [oracle.fused(f, 5, weights=w) for f in rgb]
+    got = ctx.process(frames, rip.OP_FUSED, fmt, ksize=5, weights=w)
+    for i in range(n):
+        _eq(got[i], want[i], f"tile kernel fmt {fmt} frame {i}")
+    # row bands of frame 0 through the device API
+    d_out = rip.DeviceBuffer(h * wd)
+    out = np.empty((h, wd), np.uint8)
+    for nb in (2, 5):
+        for i in range(nb):
+            o0, o1 = h * i // nb, h * (i + 1) // nb
+            i0, i1 = max(0, o0 - 3), min(h, o1 + 3)
+            d_in = rip.DeviceBuffer((i1 - i0) * wd * cn).upload(frames[0][i0:i1])
+            rip.fused_dev(d_in.ptr, d_out.ptr, wd, h, 1, fmt, 5, w, in_row0=i0, in_rows=i1 - i0, out_row0=o0, out_rows=o1 - o0)
+            out[o0:o1] = d_out.download((o1 - o0, wd))
+        _eq(out, want[0], f"tile kernel, {nb} row bands")
+
+
+@pytest.mark.parametrize("k,sigma", [(1, 1.0), (3, 0.8), (7, 2.0), (17, 6.0), (31, 9.5)])
 def test_fused_other_kernel_sizes(ctx, oracle, k, sigma):
+    """Any odd K (17x17 sigma 6 is the reference's default, ProgramHandler.hpp:9): still one launch."""
     img = synth_frame("smooth", 90, 160, 61)
     w = rip.gauss_weights(k, sigma)
+    before = rip.launch_count()
     _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=k, weights=w), oracle.fused(img, k, weights=w, threads=0), f"fused K={k}")
+    assert rip.launch_count() - before == 1
 
 
 def _adversarial(h, w):
