@@ -466,6 +466,7 @@ extern "C" int rip_stream_create(int device, rip_stream *stream)
     if (!stream) return fail(RIP_EINVAL, "rip_stream_create: NULL");
     if (int rc = check_device(device)) return rc;
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     cudaStream_t s;
     RIP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     *stream = s;
@@ -476,6 +477,7 @@ extern "C" int rip_stream_destroy(int device, rip_stream stream)
 {
     if (!stream) return RIP_OK;
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     RIP_CUDA(cudaStreamDestroy((cudaStream_t)stream));
     return RIP_OK;
 }
@@ -483,6 +485,7 @@ extern "C" int rip_stream_destroy(int device, rip_stream stream)
 extern "C" int rip_stream_sync(int device, rip_stream stream)
 {
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     RIP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return RIP_OK;
 }
@@ -491,6 +494,7 @@ extern "C" int rip_device_sync(int device)
 {
     if (int rc = check_device(device)) return rc;
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     RIP_CUDA(cudaDeviceSynchronize());
     return RIP_OK;
 }
@@ -500,6 +504,7 @@ extern "C" int rip_event_create(int device, rip_event **event)
     if (!event) return fail(RIP_EINVAL, "rip_event_create: NULL");
     if (int rc = check_device(device)) return rc;
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     cudaEvent_t e;
     RIP_CUDA(cudaEventCreate(&e));
     *event = new (std::nothrow) rip_event{device, e};
@@ -510,6 +515,7 @@ extern "C" int rip_event_destroy(rip_event *event)
 {
     if (!event) return RIP_OK;
     DeviceGuard g(event->device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", event->device);
     cudaEventDestroy(event->ev);
     delete event;
     return RIP_OK;
@@ -519,6 +525,7 @@ extern "C" int rip_event_record(rip_event *event, rip_stream stream)
 {
     if (!event) return fail(RIP_EINVAL, "rip_event_record: NULL");
     DeviceGuard g(event->device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", event->device);
     RIP_CUDA(cudaEventRecord(event->ev, (cudaStream_t)stream));
     return RIP_OK;
 }
@@ -527,6 +534,7 @@ extern "C" int rip_event_sync(rip_event *event)
 {
     if (!event) return fail(RIP_EINVAL, "rip_event_sync: NULL");
     DeviceGuard g(event->device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", event->device);
     RIP_CUDA(cudaEventSynchronize(event->ev));
     return RIP_OK;
 }
@@ -535,6 +543,7 @@ extern "C" int rip_event_elapsed_ns(rip_event *start, rip_event *stop, uint64_t 
 {
     if (!start || !stop || !ns) return fail(RIP_EINVAL, "rip_event_elapsed_ns: NULL");
     DeviceGuard g(start->device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", start->device);
     float ms = 0.f;
     RIP_CUDA(cudaEventElapsedTime(&ms, start->ev, stop->ev));
     *ns = (uint64_t)llround((double)ms * 1e6);
@@ -547,6 +556,7 @@ extern "C" int rip_malloc_device(int device, size_t bytes, void **d_ptr)
     *d_ptr = nullptr;
     if (int rc = check_device(device)) return rc;
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     RIP_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 1));
     return RIP_OK;
 }
@@ -555,6 +565,7 @@ extern "C" int rip_free_device(int device, void *d_ptr)
 {
     if (!d_ptr) return RIP_OK;
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     RIP_CUDA(cudaFree(d_ptr));
     return RIP_OK;
 }
@@ -579,6 +590,7 @@ extern "C" int rip_memcpy_h2d_async(int device, void *d_dst, const void *h_src, 
 {
     if (!d_dst || !h_src) return fail(RIP_EINVAL, "rip_memcpy_h2d_async: NULL");
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     RIP_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return RIP_OK;
 }
@@ -587,6 +599,7 @@ extern "C" int rip_memcpy_d2h_async(int device, void *h_dst, const void *d_src, 
 {
     if (!h_dst || !d_src) return fail(RIP_EINVAL, "rip_memcpy_d2h_async: NULL");
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     RIP_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return RIP_OK;
 }
@@ -595,6 +608,7 @@ extern "C" int rip_memset_device_async(int device, void *d_dst, int value, size_
 {
     if (!d_dst) return fail(RIP_EINVAL, "rip_memset_device_async: NULL");
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     RIP_CUDA(cudaMemsetAsync(d_dst, value, bytes, (cudaStream_t)stream));
     return RIP_OK;
 }
@@ -644,6 +658,7 @@ extern "C" int rip_gray(int device, rip_stream stream, const uint8_t *d_in, uint
     if (int rc = check_image("rip_gray", d_in, d_out, width, height, n_frames)) return rc;
     if (out_mode != RIP_GRAY_OUT_U8 && out_mode != RIP_GRAY_OUT_RGBA) return fail(RIP_EINVAL, "rip_gray: bad out_mode %d", out_mode);
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     return launch_gray((cudaStream_t)stream, d_in, d_out, (long long)width * height * n_frames, in_format, out_mode, device);
 }
 
@@ -655,6 +670,7 @@ extern "C" int rip_gauss(int device, rip_stream stream, const uint8_t *d_in, uin
     Weights wts;
     if (int rc = load_weights(wts, ksize, weights, "rip_gauss")) return rc;
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     return launch_blur((cudaStream_t)stream, d_in, d_out, width, height, n_frames, channels, ksize, wts, 0, height, 0, height);
 }
 
@@ -665,6 +681,7 @@ extern "C" int rip_sobel(int device, rip_stream stream, const uint8_t *d_in, uin
     if (int rc = check_image("rip_sobel", d_in, d_out, width, height, n_frames)) return rc;
     if (channels_of(in_format) == 0) return fail(RIP_EINVAL, "rip_sobel: unsupported input format %d", in_format);
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     if (fused_supported(width, height, in_format, 0, d_in, d_out))
         return launch_fused((cudaStream_t)stream, d_in, d_out, width, height, n_frames, in_format, false, nullptr, 0, height, 0,
                             height, device);
@@ -704,6 +721,7 @@ extern "C" int rip_fused(int device, rip_stream stream, const uint8_t *d_in, uin
         return fail(RIP_EINVAL, "rip_fused: input band [%d,%d) does not cover rows [%d,%d) needed for output rows [%d,%d)",
                     in_row0, in_row0 + in_rows, g0, g1, out_row0, out_row0 + out_rows);
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     cudaStream_t s = (cudaStream_t)stream;
     {
         float g3[3], thr;  // single-kernel path: 5x5, aligned shape, and weights the guard band can cover
@@ -741,6 +759,7 @@ extern "C" int rip_debug_slow_path_stats(int device, int enable, uint64_t *slow_
 {
     if (int rc = check_device(device)) return rc;
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     if (slow_pixels) *slow_pixels = 0;
     if (g_d_slow && slow_pixels) {
         unsigned long long v = 0;
@@ -782,6 +801,7 @@ extern "C" int rip_debug_selftest(int device, uint64_t *checked, uint64_t *misma
     if (!checked || !mismatches) return fail(RIP_EINVAL, "rip_debug_selftest: NULL");
     if (int rc = check_device(device)) return rc;
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     unsigned long long c = 0, m = 0;
     if (int rc = fused_selftest(device, &c, &m)) return rc;
     *checked = c;
@@ -843,6 +863,7 @@ int rip_sobel_rows(int device, cudaStream_t s, const uint8_t *d_in, uint8_t *d_o
                    int out_row0, int out_rows)
 {
     DeviceGuard g(device);
+    if (!g.ok) return fail(RIP_ENODEV, "cudaSetDevice(%d) failed", device);
     if (fused_supported(W, H, fmt, 0, d_in, d_out))
         return launch_fused(s, d_in, d_out, W, H, 1, fmt, false, nullptr, in_row0, in_rows, out_row0, out_rows, device);
     return launch_sobel(s, d_in, d_out, W, H, 1, fmt == RIP_FMT_NV12 ? RIP_FMT_GRAY8 : fmt, in_row0, in_rows, out_row0, out_rows);

@@ -108,9 +108,16 @@ blur_sep_kernel(const __grid_constant__ SepParams p, const __grid_constant__ Wei
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int K = KT ? KT : p.ksize;
     const int half = K >> 1;
-    const int tws = SEP_TW + 2 * half, th = SEP_TH + 2 * half;
-    T *tile = reinterpret_cast<T *>(smem_raw);   // [th][tws]  the input tile with halo, as fp32
+    const int tws = (SEP_TW + 2 * half + 3) & ~3, th = SEP_TH + 2 * half;   // row pitch: a multiple of 4 elements
+    const int tq = tws >> 2;
+    T *tile = reinterpret_cast<T *>(smem_raw);   // [th][tws]  the input tile with halo, as fp32, columns de-interleaved (col())
     T *hbuf = tile + th * tws;                   // [th][SEP_TW] after the horizontal pass
+    // Column c of a tile row lives at element (c % 4) * tq + c / 4: a thread of the horizontal pass produces FOUR adjacent
+    // outputs (columns 4q .. 4q+3) from K + 3 loads, and with this layout the eight threads of a quarter warp read eight
+    // consecutive 16-byte elements at every step.  (Round 1 produced one output per thread from K loads: the kernel was
+    // bound by shared-memory bandwidth -- 2.5 K 16-byte loads per pixel -- not by arithmetic: 17x17 on 16 1080p frames
+    // 2505 us, then 1244 us with the block-wide replay alone.)
+    auto col = [tq](int c) { return (c & 3) * tq + (c >> 2); };
 
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * SEP_TW, y0 = p.out_row0 + blockIdx.y * SEP_TH;
@@ -124,46 +131,100 @@ blur_sep_kernel(const __grid_constant__ SepParams p, const __grid_constant__ Wei
         const int gy_raw = y0 - half + ty;
         const bool row_ok = gy_raw <= y_last;
         const uint8_t *row = fsrc + (size_t)(clampi(gy_raw, 0, p.H - 1) - p.src_row0) * p.W * CN;
-        for (int tx = lane; tx < tws; tx += 32)
-            tile[ty * tws + tx] = row_ok ? P::load(row + (size_t)clampi(x0 - half + tx, 0, p.W - 1) * CN) : P::zero();
+        for (int tx = lane; tx < SEP_TW + 2 * half; tx += 32)
+            tile[ty * tws + col(tx)] = row_ok ? P::load(row + (size_t)clampi(x0 - half + tx, 0, p.W - 1) * CN) : P::zero();
     }
     __syncthreads();
 
-    // ---- 2. horizontal pass: hbuf[ty][x] = sum_k g[k] * tile[ty][x + k]   (one FMA chain, k ascending)
-    for (int ty = wrp; ty < th; ty += SEP_THREADS / 32) {
-        const T *t = tile + ty * tws + lane;
-        T acc = P::mul(p.g[0], t[0]);
+    // ---- 2. horizontal pass: hbuf[ty][x] = sum_k g[k] * tile[ty][x + k]   (one FMA chain per output, k ascending)
+    if (KT) {
+        const int q = lane & 7, rsub = lane >> 3;   // outputs 4q .. 4q+3 of row ty; four rows per warp instruction
+        for (int ty = wrp * 4 + rsub; ty < th; ty += SEP_THREADS / 8) {
+            const T *t = tile + ty * tws + q;
+            T acc[4];
 #pragma unroll
-        for (int k = 1; k < (KT ? KT : 1); k++) acc = P::fma(p.g[k], t[k], acc);
-        if (!KT)
-            for (int k = 1; k < K; k++) acc = P::fma(p.g[k], t[k], acc);
-        hbuf[ty * SEP_TW + lane] = acc;
-    }
-    __syncthreads();
-
-    // ---- 3. vertical pass on top of the bias, guard band, exact replay of the pixels inside it
-    const int x = x0 + lane;
-#pragma unroll 1
-    for (int oy = wrp; oy < SEP_TH; oy += SEP_THREADS / 32) {
-        const int y = y0 + oy;
-        if (y >= p.out_row0 + p.out_rows || y >= p.H) break;   // warp-uniform
-        const T *h = hbuf + oy * SEP_TW + lane;
-        T f = P::fma(p.g[0], h[0], P::splat(kSepBias));
+            for (int k = 0; k < (KT ? KT : 1) + 3; k++) {
+                const T v = t[(k & 3) * tq + (k >> 2)];   // column 4q + k
 #pragma unroll
-        for (int k = 1; k < (KT ? KT : 1); k++) f = P::fma(p.g[k], h[k * SEP_TW], f);
-        if (!KT)
-            for (int k = 1; k < K; k++) f = P::fma(p.g[k], h[k * SEP_TW], f);
-        uint32_t out = P::pack_fast(f);
-        if (P::zmin(f, p.zoff) < p.zthr) {
-            // the reference's sequence (GaussianBlur.cpp:236-258): ky-major / kx-minor from 0.0f, unfused
-            const T *t = tile + oy * tws + lane;
-            T acc = P::zero();
-            for (int ky = 0; ky < K; ky++)
-                for (int kx = 0; kx < K; kx++) acc = P::ref_step(acc, t[ky * tws + kx], wts.w[ky * K + kx]);
-            out = P::pack_exact(acc);
-            if (p.slow_counter) atomicAdd(p.slow_counter, 1ull);
+                for (int j = 0; j < 4; j++) {
+                    const int tap = k - j;
+                    if (tap == 0) acc[j] = P::mul(p.g[0], v);
+                    else if (tap > 0 && tap < (KT ? KT : 1)) acc[j] = P::fma(p.g[tap], v, acc[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) hbuf[ty * SEP_TW + 4 * q + j] = acc[j];
         }
-        if (x < p.W) P::store(fdst + ((size_t)(y - p.out_row0) * p.W + x) * CN, out);
+    } else {
+        for (int ty = wrp; ty < th; ty += SEP_THREADS / 32) {
+            const T *t = tile + ty * tws;
+            T acc = P::mul(p.g[0], t[col(lane)]);
+            for (int k = 1; k < K; k++) acc = P::fma(p.g[k], t[col(lane + k)], acc);
+            hbuf[ty * SEP_TW + lane] = acc;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. vertical pass on top of the bias and guard band: a thread produces four vertically adjacent outputs of its
+    //         column from K + 3 loads.  Every pixel stores its fast value; a pixel with a channel inside the band is
+    //         appended to a per-block list in shared memory.
+    // ---- 4. the list is replayed by the WHOLE block, one (pixel, channel) per thread.  Round 1 replayed inside the row loop:
+    //         the flagged lane ran the K*K-step chain for its four channels while the 31 others waited -- for 17x17 (band
+    //         +-88 ulps, 2 % of the pixels flagged, so every second warp-row held one) that was 1420 of the kernel's 1920
+    //         lane-instructions per pixel.  Compacted, the same chains run on all lanes at once.
+    uint16_t *list = reinterpret_cast<uint16_t *>(hbuf + th * SEP_TW);   // [SEP_TH * SEP_TW] entries oy << 5 | lane
+    __shared__ uint32_t n_list;
+    if (threadIdx.x == 0) n_list = 0;
+    __syncthreads();
+    const int x = x0 + lane;
+    {
+        const int oy0 = wrp * 4;   // SEP_TH = 32 rows = 8 warps x 4
+        const T *h = hbuf + oy0 * SEP_TW + lane;
+        T f[4];
+        if (KT) {
+#pragma unroll
+            for (int k = 0; k < (KT ? KT : 1) + 3; k++) {
+                const T v = h[k * SEP_TW];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int tap = k - j;
+                    if (tap == 0) f[j] = P::fma(p.g[0], v, P::splat(kSepBias));
+                    else if (tap > 0 && tap < (KT ? KT : 1)) f[j] = P::fma(p.g[tap], v, f[j]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                f[j] = P::fma(p.g[0], h[j * SEP_TW], P::splat(kSepBias));
+                for (int k = 1; k < K; k++) f[j] = P::fma(p.g[k], h[(j + k) * SEP_TW], f[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int oy = oy0 + j, y = y0 + oy;
+            if (y < p.out_row0 + p.out_rows && y < p.H && x < p.W) {
+                P::store(fdst + ((size_t)(y - p.out_row0) * p.W + x) * CN, P::pack_fast(f[j]));
+                if (P::zmin(f[j], p.zoff) < p.zthr) list[atomicAdd(&n_list, 1u)] = (uint16_t)(oy << 5 | lane);
+            }
+        }
+    }
+    __syncthreads();   // (also orders the fast stores above before the exact stores below, for the threads of this block)
+    const uint32_t n_items = n_list * CN;
+    if (n_items && threadIdx.x == 0 && p.slow_counter) atomicAdd(p.slow_counter, (unsigned long long)n_list);
+    const float *tf = reinterpret_cast<const float *>(tile);
+#pragma unroll 1
+    for (uint32_t it = threadIdx.x; it < n_items; it += SEP_THREADS) {
+        const uint32_t e = list[it / CN], c = it % CN, oy = e >> 5, ox = e & 31u;
+        // the reference's sequence (GaussianBlur.cpp:236-258) for one channel: ky-major / kx-minor from 0.0f, unfused
+        float acc = 0.0f;
+        for (int ky = 0; ky < K; ky++) {
+            const float *tr = tf + (size_t)(oy + ky) * tws * CN + c;
+            const float *wr = wts.w + ky * K;
+#pragma unroll 4
+            for (int kx = 0; kx < K; kx++) acc = __fadd_rn(acc, __fmul_rn(tr[col((int)ox + kx) * CN], wr[kx]));
+        }
+        const uint32_t v = (uint32_t)__float2int_rz(fminf(fmaxf(acc, 0.f), 255.f));   // (uchar)clamp(sum, 0, 255), GaussianBlur.cpp:255-258
+        fdst[((size_t)(y0 + (int)oy - p.out_row0) * p.W + (x0 + (int)ox)) * CN + c] = (uint8_t)v;
     }
 }
 
@@ -175,35 +236,40 @@ unsigned long long *g_sep_slow_counter = nullptr;
 
 void blur_sep_set_slow_counter(unsigned long long *d_counter) { g_sep_slow_counter = d_counter; }
 
-// Separable taps and the guard band for them.  With u = 2^-24, all weights >= 0, sum = sum(w), pixel values <= 255:
-//   reference:  acc_k = fl(acc_{k-1} + fl(p_k w_k)); each add errs by <= u |acc_k| <= u 255 (w_0 + .. + w_k), each
-//               product by <= u 255 w_k:   |S_ref - S| <= u 255 (sum_i w_i (K*K - i) + sum)
+// half an ulp of the fp32 binade that holds x (x > 0): the largest rounding error of a result whose magnitude is <= x
+static double hulp(double x) { return x > 0.0 ? std::ldexp(1.0, (int)std::floor(std::log2(x)) - 24) : 0.0; }
+
+// Separable taps and the guard band for them.  All weights >= 0, pixel values <= 255, W_k = w_0 + .. + w_k:
+//   reference:  acc_k = fl(acc_{k-1} + fl(p_k w_k)), acc_0 = fl(p_0 w_0): every rounding is bounded by half an ulp of the
+//               binade its result can reach (as in rip_fused.cu; round 1 used u |value|, up to twice as much):
+//               |S_ref - S| <= sum_k hulp(255 w_k) + sum_{k>=1} hulp(255 W_k)
 //   separable model:  |S - S_sep| <= 255 sum_ij |w_ij - g_i g_j|            (S_sep = the exact separable sum)
-//   horizontal FMA chain: result k is <= 255 G_k (G_k = g_0 + .. + g_k) and rounded once: error <= u 255 sum_k G_k,
+//   horizontal FMA chain: result k is <= 255 G_k (G_k = g_0 + .. + g_k) and rounded once: error <= sum_k hulp(255 G_k),
 //               which the vertical taps scale by sum(g)
 //   vertical FMA chain on top of the bias: every result lies in [256, 512) and is rounded on that binade's 2^-16
 //               half-ulp: <= K 2^-16 (the last of them is the +1/2 in `a` below; counted here as well)
 //   margin 2 % + 1e-6 on top.
 static bool plan_sep_blur(const float *w, int K, float *g, double *band_out)
 {
-    double sum = 0.0, cum = 0.0;
+    const double up = 1.0 + 1e-6;   // (bounds that sit just below a power of two are pushed into the next binade: safe side)
+    double sum = 0.0, b_ref = 0.0;
     for (int i = 0; i < K * K; i++) {
         if (!(w[i] >= 0.0f) || !std::isfinite(w[i])) return false;
         sum += (double)w[i];
-        cum += (double)w[i] * (K * K - i);
+        b_ref += hulp(255.0 * (double)w[i] * up);
+        if (i >= 1) b_ref += hulp(255.0 * sum + 1e-3);   // (+1e-3: the computed partial sums carry their own errors)
     }
     if (!(sum > 0.0) || 255.0 * sum >= 255.9) return false;   // floor(S) must stay <= 255
     for (int k = 0; k < K; k++) g[k] = (float)std::sqrt((double)w[k * K + k]);
-    double dev = 0.0, gsum = 0.0, gpart = 0.0, gcum = 0.0;
+    double dev = 0.0, gsum = 0.0, gpart = 0.0, b_h = 0.0;
     for (int i = 0; i < K; i++)
         for (int j = 0; j < K; j++) dev += std::fabs((double)w[i * K + j] - (double)g[i] * (double)g[j]);
     for (int k = 0; k < K; k++) {
         gsum += (double)g[k];
         gpart += (double)g[k];
-        gcum += gpart;
+        b_h += hulp(255.0 * gpart * up);
     }
-    const double u = std::ldexp(1.0, -24);
-    const double band = (255.0 * dev + u * 255.0 * (cum + sum) + u * 255.0 * gcum * gsum + K * std::ldexp(1.0, -16)) * 1.02 + 1e-6;
+    const double band = (255.0 * dev + b_ref + b_h * gsum + K * std::ldexp(1.0, -16)) * 1.02 + 1e-6;
     if (band > 0.05) return false;   // not (close to) a symmetric separable kernel: the exact kernel handles it
     *band_out = band;
     return true;
@@ -272,7 +338,8 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
     }
     const int half = ksize >> 1;
     const size_t elem = cn == 4 ? sizeof(float4) : sizeof(float);
-    const size_t smem = ((size_t)(SEP_TH + 2 * half) * (SEP_TW + 2 * half) + (size_t)(SEP_TH + 2 * half) * SEP_TW) * elem;
+    const size_t smem = ((size_t)(SEP_TH + 2 * half) * ((SEP_TW + 2 * half + 3) & ~3) + (size_t)(SEP_TH + 2 * half) * SEP_TW) * elem +
+                        (size_t)SEP_TH * SEP_TW * sizeof(uint16_t);   // tile, horizontal pass, list of guard-band pixels
     const dim3 grid((W + SEP_TW - 1) / SEP_TW, (out_rows + SEP_TH - 1) / SEP_TH, n_frames);
     if (grid.y > 65535u || grid.z > 65535u) return RIP_EUNSUPPORTED;
     return cn == 4 ? launch_sep_cn<4>(s, p, wts, grid, smem) : launch_sep_cn<1>(s, p, wts, grid, smem);
