@@ -1133,14 +1133,25 @@ extern "C" int rip_submit(rip_ctx *ctx, const rip_op_desc *desc, const uint8_t *
     const int units = banded ? height : n_frames;
     const int used = units < nd ? units : nd;
     const int halo = desc->op == RIP_OP_FUSED ? desc->ksize / 2 + 1 : 1;
-    t->n_parts = used;
-    t->remaining = used;
+    // Row-band mode: a device's band is cut further into `sub` consecutive sub-bands (each with its own halo rows) that go
+    // through the device's buffer sets one after the other, so the upload of sub-band i+1 overlaps the kernel of sub-band i
+    // and the download of sub-band i-1 -- one 8K frame on one device is otherwise a strictly serial H2D, kernel, D2H.
+    int sub = 1;
+    if (banded) {
+        const size_t band_bytes = (size_t)width * t->cn * ((size_t)height / (size_t)used + 1);
+        sub = (int)(band_bytes / ((size_t)12 << 20));
+        sub = sub < 1 ? 1 : sub > 4 ? 4 : sub;
+        if (height / (used * sub) < 64) sub = 1;
+    }
+    const int n_parts = used * sub;
+    t->n_parts = n_parts;
+    t->remaining = n_parts;
     std::vector<Part *> parts;
-    for (int i = 0; i < used; i++) {
+    for (int i = 0; i < n_parts; i++) {
         Part *p = new Part();
         p->t = t.get();
         p->index = i;
-        if (banded) rip_band_rows(height, used, i, halo, &p->in_row0, &p->in_rows, &p->out_row0, &p->out_rows);
+        if (banded) rip_band_rows(height, n_parts, i, halo, &p->in_row0, &p->in_rows, &p->out_row0, &p->out_rows);
         else {
             int fc = 0;
             rip_shard_frames(n_frames, used, i, &p->f0, &fc);
@@ -1153,7 +1164,7 @@ extern "C" int rip_submit(rip_ctx *ctx, const rip_op_desc *desc, const uint8_t *
         DevState &d = *ctx->devs[i];
         {
             std::lock_guard<std::mutex> lk(d.mu);
-            d.queue.push_back(parts[i]);
+            for (int k = 0; k < sub; k++) d.queue.push_back(parts[i * sub + k]);
         }
         d.cv.notify_one();
     }

@@ -222,7 +222,19 @@ static int launch_fused_x2_n(cudaStream_t s, FusedParams p, int n_frames, int fm
         xp.bias = (float)(256.0 + a * ulp);
         xp.zthr = (2u * a) << (32 - kFracBits);
         for (int i = 0; i < 25; i++) xp.fix.ws[i] = std::ldexp(p.w[i], 100);   // (exact: w >= 2^-70 or 0, checked in plan_weights_band)
-        plan_flat_table(p.w, xp.fix.flat_dec);
+        {   // (256 x 25 host operations: keep the last table)
+            static std::mutex mu;
+            static float last_w[25];
+            static uint32_t last_tab[8];
+            static bool have = false;
+            std::lock_guard<std::mutex> lk(mu);
+            if (!have || memcmp(last_w, p.w, sizeof(last_w)) != 0) {
+                plan_flat_table(p.w, last_tab);
+                memcpy(last_w, p.w, sizeof(last_w));
+                have = true;
+            }
+            memcpy(xp.fix.flat_dec, last_tab, sizeof(last_tab));
+        }
     }
     const long long blocks = (long long)n_frames * p.n_segs * p.n_band_groups;
     if (blocks <= 0 || blocks > 0x7fffffffLL) return fail(RIP_EINVAL, "rip_fused: grid of %lld blocks is out of range", blocks);

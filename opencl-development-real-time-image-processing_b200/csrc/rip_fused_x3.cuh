@@ -300,8 +300,6 @@ struct GeoX {
     int adv_lo, adv_n;       // the source pointer advances before the load of step r iff 0 <= r - adv_lo < adv_n
     uint32_t pf_off;         // byte offset from src of the line this lane prefetches into L2 (0: none)
     int lane;
-    uint32_t lane_cols;      // lane | cmin << 5 | cmax << 15, cmin / cmax = first / last column of the band (0 = pixel 0 of lane 0)
-                             // that lies inside the image
     uint32_t need;           // pixels of this lane whose blurred value feeds an output (bit j = pixel j): all of lanes 1..30,
                              // only the pixel next to the band in the two halo lanes, none in lanes outside the image
     bool e_left, e_right;    // this lane holds image column 0 / W-1 (border rules in x apply to it)
@@ -320,32 +318,62 @@ struct GeoX {
 // (1) constant neighbourhood: if the 5 rows x (NPX + 4) columns around the lane's pixels all hold one gray value v, every
 // 5x5 window of the lane is that constant and the answer is bit v of xp.flat_dec, which the host evaluated with the
 // reference's own sequence for the weights in use.  Returns 0 / 1 = the answer, 2 = the neighbourhood is not constant.
+// `hist` (one word per lane in shared memory: a register that lives across the row loop costs the hot path 16 moves per trip, measured)
+// remembers the last row at which this test found the lane's 12 columns of the NEWEST ring row constant, the
+// value, and for how many consecutive rows that has held (row << 12 | run << 8 | value): inside a constant region the test then
+// reads one ring row per image row instead of five (flat content: 945 -> see profiles/README.md).  A row that did not come
+// through here breaks the run (its row number is missing), so the history never claims more than was checked.
+// Per-lane table in shared memory, filled once per block (fused_x2_kernel): words 0 .. NPX+3 = byte offset, relative to the lane's
+// own 16 bytes in plane 0 of a ring row, of the ring word of the pixel `rel - 2` columns from the lane's first pixel, with the
+// clamp-to-edge rule of the lane that holds an image border already applied (GaussianBlur.cpp:240); word 15 = `hist`.  The cold
+// paths read their column offsets from here: no constant-memory look-ups, no min / max, no border branch in the row bodies (the
+// main loop holds three copies of every cold block, and its size costs time even when the blocks never run).
+constexpr int kLaneTabWords = 16;
+__shared__ uint32_t s_lane_tab[kWarpsPerBlock * 32 * kLaneTabWords];
+
 template <int NPX>
-__device__ RIP_REPLAY_FN uint32_t blur_flat_lane(uint32_t ring0, uint32_t newest, uint32_t lane_cols, const uint32_t *flat_dec)
+__device__ RIP_REPLAY_FN uint32_t blur_flat_lane(uint32_t ring_lane, uint32_t newest, uint32_t tab, const uint32_t *flat_dec, int r)
 {
     constexpr uint32_t kRowB = 32 * NPX * 4;
-    const int lane = (int)(lane_cols & 31u), cmin = (int)((lane_cols >> 5) & 0x3ffu), cmax = (int)(lane_cols >> 15);
-    const int col0 = NPX * lane;
-    const uint32_t ol2 = ring_off<NPX>((uint32_t)max(col0 - 2, cmin)), ol1 = ring_off<NPX>((uint32_t)max(col0 - 1, cmin));
-    const uint32_t or0 = ring_off<NPX>((uint32_t)min(col0 + NPX, cmax)), or1 = ring_off<NPX>((uint32_t)min(col0 + NPX + 1, cmax));
-    const uint32_t own = 16u * (uint32_t)lane;
-    uint32_t row = ring0 + newest * kRowB;
-    const uint32_t v = lds_u32(row + own);
-    uint32_t diff = 0;
-#pragma unroll 1
-    for (int k = 0; k < 5; k++) {
+    const uint32_t ol2 = lds_u32(tab), ol1 = lds_u32(tab + 4u), or0 = lds_u32(tab + 4u * (NPX + 2)), or1 = lds_u32(tab + 4u * (NPX + 3));
+    const uint32_t hist_addr = tab + 4u * (kLaneTabWords - 1);
+    const uint32_t v = lds_u32(ring_lane + newest * kRowB);
+    // do the lane's NPX + 4 columns of the ring row at `row` (this lane's plane-0 address) all hold v?  (0 = yes)
+    auto row_diff = [&](uint32_t row) -> uint32_t {
+        uint32_t diff = 0;
 #pragma unroll
         for (int pl = 0; pl < NPX / 4; pl++) {
             uint32_t a, b, c, d;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(row + own + 512 * pl));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(row + 512 * pl));
             diff |= (a ^ v) | (b ^ v);
             diff |= (c ^ v) | (d ^ v);
         }
         diff |= (lds_u32(row + ol2) ^ v) | (lds_u32(row + ol1) ^ v);
         diff |= (lds_u32(row + or0) ^ v) | (lds_u32(row + or1) ^ v);
-        row = row == ring0 ? ring0 + ((uint32_t)kRing - 1u) * kRowB : row - kRowB;
+        return diff;
+    };
+    const uint32_t rr = (uint32_t)r & 0xfffffu, prev = (uint32_t)(r - 1) & 0xfffffu;
+    const uint32_t hist = lds_u32(hist_addr);
+    const uint32_t known = ((hist >> 12) == prev && (hist & 0xffu) == v) ? ((hist >> 8) & 15u) : 0u;   // rows r-1 .. r-known are constant v
+    // row r, then the rows nobody has looked at yet: r-known-1 .. r-4 (only at the first rows of a constant region)
+    uint32_t k = 0u, new_hist = 0u, ans = 2u;
+#pragma unroll 1
+    for (;;) {
+        const uint32_t s = newest >= k ? newest - k : newest + (uint32_t)kRing - k;
+        if (row_diff(ring_lane + s * kRowB)) {
+            if (k) new_hist = rr << 12 | k << 8 | v;   // rows r .. r-k+1 are constant
+            break;
+        }
+        k = k == 0u ? known + 1u : k + 1u;
+        if (k >= 5u) {
+            const uint32_t rows_ok = known >= 4u ? known + 1u : 5u;   // consecutive constant rows ending at row r
+            new_hist = rr << 12 | (rows_ok > 8u ? 8u : rows_ok) << 8 | v;
+            ans = (flat_dec[v >> 5] >> (v & 31u)) & 1u;
+            break;
+        }
     }
-    return diff ? 2u : (flat_dec[v >> 5] >> (v & 31u)) & 1u;
+    sts_u32(hist_addr, new_hist);
+    return ans;
 }
 
 // byte offset, relative to the lane's own 16 bytes in plane 0, of the ring word of the pixel `rel - 2` columns from
@@ -372,31 +400,23 @@ __constant__ RingRel<4> c_ring_rel4;
 // 2^100: fl(q*2^-149 * w*2^100) = fl(q * w) * 2^-49 exactly (same mantissa, results stay normal), likewise every partial
 // sum, so the scaled chain rounds exactly like the reference's (ky-major / kx-minor from 0.0f, unfused) and needs no
 // integer-to-float conversion.  `rowaddr[i]` = shared-memory address of this lane's 16 bytes (plane 0) of gray row r - i;
-// in the main loop those are compile-time offsets from two registers, so the 25 loads need ten address adds.  Columns
-// are clamped to the image (clamp-to-edge, GaussianBlur.cpp:240) only in the two lanes that hold column 0 / W-1.
+// in the main loop those are compile-time offsets from two registers, so the 25 loads need ten address adds.  The column
+// offsets come from the lane's table (s_lane_tab), clamp-to-edge included.
 // What an excursion costs is its executed instruction count (the kernel's time is its warp-instruction count at a steady
 // ~65 % issue rate, profiles/README.md), so everything that is not the 25 loads, 25 products and 25 adds is kept short.
 // (Out of line -- one __noinline__ copy for all row bodies, main loop 1126 instead of 1693 instructions -- was measured:
 // 445 us against 431 us; the call sequence and the run-time ring slots cost more than the smaller loop gains.)
 template <int NPX>
-__device__ RIP_REPLAY_FN uint32_t blur_replay_lane(uint32_t my, const uint32_t (&rowaddr)[5], bool edge_lane, uint32_t lane_cols, const BlurFixConst &cst)
+__device__ RIP_REPLAY_FN uint32_t blur_replay_lane(uint32_t my, const uint32_t (&rowaddr)[5], uint32_t tab, const BlurFixConst &cst)
 {
-    const int *lut = NPX == 8 ? c_ring_rel8.v : c_ring_rel4.v;
     uint32_t dec = 0;
 #pragma unroll 1
     while (my) {
         const uint32_t j = (uint32_t)__ffs(my) - 1u;
         my &= my - 1u;
         uint32_t off[5];
-        if (edge_lane) {
-            const int lane = (int)(lane_cols & 31u), cmin = (int)((lane_cols >> 5) & 0x3ffu), cmax = (int)(lane_cols >> 15);
-            const int rel_lo = cmin - NPX * lane + 2, rel_hi = cmax - NPX * lane + 2;   // clamp-to-edge in lane-relative columns
 #pragma unroll
-            for (int kx = 0; kx < 5; kx++) off[kx] = (uint32_t)lut[min(max((int)j + kx, rel_lo), rel_hi)];
-        } else {
-#pragma unroll
-            for (int kx = 0; kx < 5; kx++) off[kx] = (uint32_t)lut[j + kx];
-        }
+        for (int kx = 0; kx < 5; kx++) off[kx] = lds_u32(tab + 4u * j + 4u * kx);   // columns j-2 .. j+2 of the lane, clamped to the image
         float g25[25];
 #pragma unroll
         for (int ky = 0; ky < 5; ky++)
@@ -584,10 +604,11 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
 #else
             if (flagged) {
                 // which pixels are inside the band ... and feed an output
-                // (a pixel whose masked value is n = 0 needs no fix: the reference's result is n or n - 1 and cannot be negative.
-                // Black bars and black frames leave here.)
-                uint32_t my = 0;
+                // Which pixels are inside the band and feed an output?  A pixel whose masked value is n = 0 needs no fix at all: the
+                // reference's result is n or n - 1 and cannot be negative (black bars and frames leave here).
                 const uint32_t zero_bits = __float_as_uint(kBias);
+                const uint32_t tab = (uint32_t)__cvta_generic_to_shared(&s_lane_tab[threadIdx.x * kLaneTabWords]);
+                uint32_t my = 0, dec = 2u;
 #pragma unroll
                 for (int j = 0; j < NP; j++) {
                     const uint32_t l = lo2u(F[j]), h = hi2u(F[j]);
@@ -595,23 +616,22 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
                     my |= (((h << (32 - kFracBits)) < xp.zthr && (h & kBiasMask) != zero_bits) ? 1u : 0u) << (j + NP);
                 }
                 my &= geo.need;
-                if (my) {
-                    uint32_t dec = 2u;
-                    // constant regions: every pixel of the lane is inside the band and the fast path's values are bit-identical
-                    // (a cheap necessary condition); then one table bit answers for all of them.  A lane-divergent branch that
-                    // textured content does not take.
-                    if (my == (1u << NPX) - 1u) {
-                        uint32_t same = 0;
+                // Constant regions: every pixel of the lane is inside the band and the fast path's values are bit-identical (a cheap
+                // necessary condition); then one table bit answers for all of them if the ring confirms that the neighbourhood is
+                // one gray value.  A lane-divergent branch that textured content does not take.  (Testing for identical values
+                // BEFORE building the mask makes flat content another 3 % faster and textured content 2.5 % slower: measured.)
+                if (my == (1u << NPX) - 1u) {
+                    uint32_t same = 0;
 #pragma unroll
-                        for (int j = 0; j < NP; j++) same |= (lo2u(F[j]) ^ lo2u(F[0])) | (hi2u(F[j]) ^ lo2u(F[0]));
-                        if (same == 0u) {
-                            const uint32_t ring0 = geo.ring_lane - 16u * (uint32_t)geo.lane, newest = (rowaddr[0] - geo.ring_lane) / kRowB;
-                            dec = blur_flat_lane<NPX>(ring0, newest, geo.lane_cols, xp.fix.flat_dec);
-                            if (dec == 1u) dec = my;
-                        }
+                    for (int j = 0; j < NP; j++) same |= (lo2u(F[j]) ^ lo2u(F[0])) | (hi2u(F[j]) ^ lo2u(F[0]));
+                    if (same == 0u) {
+                        dec = blur_flat_lane<NPX>(geo.ring_lane, (rowaddr[0] - geo.ring_lane) / kRowB, tab, xp.fix.flat_dec, r);
+                        if (dec == 1u) dec = my;
                     }
+                }
+                if (my) {
                     // the general case: the reference's sequence for each pixel inside the band
-                    if (dec == 2u) dec = blur_replay_lane<NPX>(my, rowaddr, geo.e_left || geo.e_right, geo.lane_cols, xp.fix);
+                    if (dec == 2u) dec = blur_replay_lane<NPX>(my, rowaddr, tab, xp.fix);
                     if constexpr (STATS) {
                         if (p.slow_counter) atomicAdd(p.slow_counter, (unsigned long long)__popc(my));
                     }
@@ -806,7 +826,16 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     geo.e_left = (band == 0) && geo.lane == 1;
     geo.e_right = geo.lane == lane_last;
     geo.edge_warp = band == 0 || lane_last <= 31;
-    geo.lane_cols = (uint32_t)geo.lane | (uint32_t)(band == 0 ? NPX : 0) << 5 | (uint32_t)(min(lane_last, 31) * NPX + NPX - 1) << 15;
+    if constexpr (BLUR) {
+        // this lane's column table for the cold paths (read and written by its own lane only: no barrier)
+        const int cmin = band == 0 ? NPX : 0, cmax = min(lane_last, 31) * NPX + NPX - 1;   // first / last band column inside the image (0 = pixel 0 of lane 0)
+        const int rel_lo = cmin - NPX * geo.lane + 2, rel_hi = cmax - NPX * geo.lane + 2;   // the same in lane-relative columns
+        const int *lut = NPX == 8 ? c_ring_rel8.v : c_ring_rel4.v;
+        uint32_t *tab = &s_lane_tab[threadIdx.x * kLaneTabWords];
+#pragma unroll 1
+        for (int rel = 0; rel < NPX + 4; rel++) tab[rel] = (uint32_t)lut[min(max(min(max(rel, rel_lo), rel_hi), 0), NPX + 3)];   // (lanes outside the image: any valid entry)
+        tab[kLaneTabWords - 1] = 0u;   // blur_flat_lane's history
+    }
     geo.need = !in_img ? 0u : geo.lane == 0 ? 1u << (NPX - 1) : geo.lane == 31 ? 1u : (1u << NPX) - 1u;
     const int ys = p.out_row0 + seg * p.seg_rows;
     const int ye = min(ys + p.seg_rows, p.out_row0 + p.out_rows);

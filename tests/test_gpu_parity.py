@@ -165,13 +165,19 @@ def test_blur_guard_band_statistics_and_non_separable_weights(ctx, oracle):
     h, wd = 96, 160
     d_out = rip.DeviceBuffer(h * wd * 4)
     w = rip.gauss_weights(5, 1.0)
-    for kind, lo, hi in (("uniform", 1e-5, 2e-2), ("flat", 0.9, 1.1)):
-        img = synth_frame("uniform", h, wd, 72, 4) if kind == "uniform" else np.full((h, wd, 4), 77, np.uint8)
+    # "flat": a constant tile takes its results from the constant-window table, no replay at all (every real RGBA frame has such a
+    # channel: alpha); "speckled": constant but for one pixel per 16 x 16 block, so no tile is constant while nearly every window
+    # still is -- those pixels sit inside the guard band and are replayed
+    speck = np.full((h, wd, 4), 77, np.uint8)
+    speck[5::16, 7::16] = 200
+    for kind, lo, hi in (("uniform", 1e-5, 2e-2), ("flat", 0.0, 0.0), ("speckled", 0.5, 1.1)):
+        img = synth_frame("uniform", h, wd, 72, 4) if kind == "uniform" else np.full((h, wd, 4), 77, np.uint8) if kind == "flat" else speck
         d_in = rip.DeviceBuffer(img.nbytes).upload(img)
         rip.slow_path_stats(True)
         rip.gauss_dev(d_in.ptr, d_out.ptr, wd, h, 1, 4, 5, w)
         frac = rip.slow_path_stats(False) / (h * wd)
         assert lo <= frac <= hi, (kind, frac)
+        _eq(d_out.download((h, wd, 4)), oracle.blur(img, 5, weights=w), f"blur {kind}")
     rng = np.random.default_rng(5)
     wr = rng.random((5, 5)).astype(np.float32)
     wr /= wr.sum() * np.float32(1.001)
@@ -179,6 +185,24 @@ def test_blur_guard_band_statistics_and_non_separable_weights(ctx, oracle):
     rip.slow_path_stats(True)
     _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=5, weights=wr), oracle.blur(img, 5, weights=wr, threads=0), "random weights")
     assert rip.slow_path_stats(False) == 0   # the separable kernel did not run
+
+
+@pytest.mark.parametrize("k,sigma,stream", [(5, 1.0, 0), (5, 1.5, 0), (9, 2.5, 0), (17, 6.0, 0), (5, 1.0, 1), (5, 1.5, 1)])
+def test_blur_constant_channels_take_the_table(ctx, oracle, k, sigma, stream, opt):
+    """Real RGBA frames: alpha is 255 throughout, sky is black, highlights are clipped.  A constant channel's fast sum sits on an
+    integer -- inside the guard band for every pixel -- so its result comes from the host-evaluated constant-window table
+    (tile-wide in the tiled kernel, per lane neighbourhood in the streaming kernel); the other channels are untouched."""
+    opt("RIP_BLUR_STREAM" if stream else "RIP_BLUR_TILED", 1)
+    h, wd = 130, 200
+    img = synth_frame("uniform", h, wd, 123, 4)
+    img[..., 3] = 255                      # alpha
+    img[: h // 3, :, :3] = 0               # black sky
+    img[h // 3: h // 2, : wd // 2, 1] = 255  # one clipped channel in a region
+    img[-20:, -70:] = (13, 13, 13, 255)    # a flat patch that ends at the image corner
+    w = rip.gauss_weights(k, sigma)
+    _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), oracle.blur(img, k, weights=w, threads=0), f"constant channels K={k}")
+    g = np.ascontiguousarray(img[..., 1])
+    _eq(ctx.process(g, rip.OP_GAUSSIAN, rip.FMT_GRAY8, ksize=k, weights=w), oracle.blur(g, k, weights=w, threads=0), f"constant regions, gray K={k}")
 
 
 def test_blur_rejects_bad_arguments(ctx):

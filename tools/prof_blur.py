@@ -15,6 +15,11 @@ launches = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 rng = np.random.default_rng(1)
 h, w = 1080, 1920
 img = rng.integers(0, 256, (n, h, w, 4), dtype=np.uint8)
+if len(sys.argv) > 5 and sys.argv[5] == "alpha255":   # what real RGBA frames look like: a constant alpha channel
+    img[..., 3] = 255
+if len(sys.argv) > 5 and sys.argv[5] == "sky":        # alpha 255 and the upper half black (the reference's Artemis_* images)
+    img[..., 3] = 255
+    img[:, : h // 2, :, :3] = 0
 d_in = rip.DeviceBuffer(img.nbytes).upload(img)
 d_out = rip.DeviceBuffer(img.nbytes)
 wt = rip.gauss_weights(k, sigma)
@@ -25,4 +30,4 @@ for i in range(launches):
     ts.append(e0.elapsed_ns(e1) / 1e3)
 us = sorted(ts[1:] or ts)[len(ts[1:] or ts) // 2]
 px = n * h * w
-print(f"gauss {k}x{k} sigma {sigma} on {n} x {w}x{h} RGBA: {us:.1f} us ({px / us:.0f} Mpx/s, {px * 8 / us / 1e3:.0f} GB/s algorithmic)")
+print(f"gauss {k}x{k} sigma {sigma} on {n} x {w}x{h} RGBA {sys.argv[5] if len(sys.argv) > 5 else 'noise'}: {us:.1f} us ({px / us:.0f} Mpx/s, {px * 8 / us / 1e3:.0f} GB/s algorithmic)")
