@@ -1,3 +1,6 @@
 #!/bin/bash
-python -m pytest tests -m gpu -x -q 2>&1 | tail -n 25
-for c in noise alpha255 sky; do python tools/prof_blur.py 5 1.0 16 4 $c; done
+for lib in default tools/ab/*.so; do
+  echo "== $lib"
+  if [ $lib != default ]; then export RIP_LIB_PATH=$PWD/$lib; else unset RIP_LIB_PATH; fi
+  RIP_FUSED_NPX=4 python tools/prof_fused.py --frames 32 --launches 8
+done
