@@ -41,6 +41,7 @@ struct SepParams {
     int W, H, src_row0, src_rows, out_row0, out_rows, ksize;
     uint32_t zoff, zthr;        // replay iff ((bits << 17) + zoff) < zthr
     float g[RIP_MAX_KSIZE];     // separable taps
+    float sgv[5], sgh[5], sbias;   // streaming 5x5 kernel: vertical taps * 2^75, horizontal taps * 2^74, bias 256 + a * 2^-15
     uint8_t flat[256];          // flat[v] = the reference's result for a CONSTANT KxK window of value v (its own sequence, host-evaluated)
     unsigned long long *slow_counter;   // optional statistics (NULL in production)
 };
@@ -382,6 +383,13 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
     const uint32_t a = (uint32_t)std::ceil(band / ulp + 0.5);
     p.zoff = a << (32 - kSepFracBits);
     p.zthr = (2u * a) << (32 - kSepFracBits);
+    if (ksize == 5) {
+        for (int k = 0; k < 5; k++) {
+            p.sgv[k] = std::ldexp(p.g[k], 75);
+            p.sgh[k] = std::ldexp(p.g[k], 74);
+        }
+        p.sbias = (float)(256.0 + a * ulp);
+    }
     // 5x5 RGBA: the streaming kernel for large inputs (1.4x the tiled kernel on 16 1080p frames), the tiled one for
     // small ones, where a block per 32x32 tile exposes more parallelism (one 683x1023 frame: 25 us against 31 us)
     const bool big = (long long)n_frames * out_rows * W >= (2LL << 20);

@@ -25,23 +25,29 @@ __device__ __forceinline__ uint32_t bs_lo(bs_u64 v) { uint32_t lo, hi; asm("mov.
 __device__ __forceinline__ uint32_t bs_hi(bs_u64 v) { uint32_t lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); return hi; }
 __device__ __forceinline__ bs_u64 bs_fma2(bs_u64 a, bs_u64 b, bs_u64 c) { bs_u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ bs_u64 bs_mul2(bs_u64 a, bs_u64 b) { bs_u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ bs_u64 bs_add2_rm(bs_u64 a, bs_u64 b) { bs_u64 d; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ bs_u64 bs_pk2u(uint32_t lo, uint32_t hi) { bs_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
 
 constexpr int kBsWarps = 4;          // warps per block, each an independent band
 constexpr int kBsBand = 60;          // output columns per warp
 constexpr int kBsRowB = 32 * 32;     // bytes of one shared V row (32 lanes x 4 pairs)
 
-// u8 -> fp32 of two channels of a packed pixel: 0x4B000000 | byte is the float 8388608 + byte
+// Two channels of a packed pixel as a pair of INTEGER BIT PATTERNS: the isolated byte q, read as a float, is the denormal
+// q * 2^-149, which the vertical FMAs consume at full rate; the vertical taps carry 2^75 and the horizontal taps 2^74
+// (powers of two: every rounding is unchanged), so no conversion instruction runs at all (round 1: PRMT + FADD per channel).
 __device__ __forceinline__ bs_u64 bs_cvt2(uint32_t px, uint32_t sel_lo, uint32_t sel_hi)
 {
-    const float m = 8388608.0f;
-    return bs_pk2(__uint_as_float(__byte_perm(px, 0x4B000000u, sel_lo)) - m, __uint_as_float(__byte_perm(px, 0x4B000000u, sel_hi)) - m);
+    return bs_pk2u(__byte_perm(px, 0u, sel_lo), __byte_perm(px, 0u, sel_hi));
 }
 
-// floor of the four channels of one pixel (mantissa bits 15..22 of the biased sums) packed into a u32
+// floor of the four channels of one pixel packed into a u32.  The biased sums lie in [256, 512); adding 2^23 - 256 rounded toward
+// minus infinity leaves 2^23 + floor(sum - 256), whose low byte is the result: one packed add per channel pair, then a byte gather
+// (round 1: a shift per channel before the gather).
 __device__ __forceinline__ uint32_t bs_pack(bs_u64 c01, bs_u64 c23)
 {
-    const uint32_t a = bs_lo(c01) >> kSepFracBits, b = bs_hi(c01) >> kSepFracBits, c = bs_lo(c23) >> kSepFracBits, d = bs_hi(c23) >> kSepFracBits;
-    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+    const float m = 8388608.0f - kSepBias;
+    const bs_u64 M = bs_pk2(m, m), t01 = bs_add2_rm(c01, M), t23 = bs_add2_rm(c23, M);
+    return __byte_perm(__byte_perm(bs_lo(t01), bs_hi(t01), 0x0040), __byte_perm(bs_lo(t23), bs_hi(t23), 0x0040), 0x5410);
 }
 
 // the reference's sequence for one pixel (GaussianBlur.cpp:236-258): column `col` of the warp's ring, rows oldest first
@@ -73,17 +79,9 @@ __device__ __noinline__ uint32_t bs_replay(uint32_t ring, uint32_t cur_slot, uin
 // 16 1080p frames with alpha = 255 took 977 us against 219 us for frames whose alpha is noise.
 // Returns the patched outputs in .x / .y and in .z which pixels still need the replay (bit 0 / bit 1); the caller runs it, so that
 // the call depth -- and with it the kernel's register allocation -- stays what it was.
-__device__ __noinline__ uint3 bs_fix(uint32_t ring, uint32_t cur_slot, uint32_t lane, bool store1, bs_u64 f0, bs_u64 f1, bs_u64 f2, bs_u64 f3,
-                                     const SepParams &p, uint32_t o0, uint32_t o1)
+__device__ __noinline__ uint3 bs_fix(uint32_t ring, uint32_t cur_slot, uint32_t lane, uint32_t fm /* flagged channels: bits 0-3 pixel 0, bits 4-7 pixel 1 */,
+                                     const uint8_t *flat, uint32_t o0, uint32_t o1)
 {
-    const uint8_t *flat = p.flat;
-    uint32_t fm = 0;   // flagged channels: bits 0-3 pixel 0, bits 4-7 pixel 1
-    {
-        const uint32_t b[8] = {bs_lo(f0), bs_hi(f0), bs_lo(f1), bs_hi(f1), bs_lo(f2), bs_hi(f2), bs_lo(f3), bs_hi(f3)};
-#pragma unroll
-        for (int k = 0; k < 8; k++) fm |= (((b[k] << (32 - kSepFracBits)) + p.zoff) < p.zthr ? 1u : 0u) << k;
-        if (!store1) fm &= 0xfu;
-    }
     const uint32_t a0 = ring + 8u * lane - 8u;   // columns 2 lane - 2 .. 2 lane + 3 of a ring row (lanes 1..30: inside the row)
     uint32_t ref, diff = 0;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ref) : "r"(a0 + cur_slot * 256u + 8u));
@@ -139,9 +137,15 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const __grid_constant__
 
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(&ring_s[warp][0][0]);
     const uint32_t vrow = (uint32_t)__cvta_generic_to_shared(&vrow_s[warp][0][0]);
-    const bs_u64 G0 = bs_pk2(p.g[0], p.g[0]), G1 = bs_pk2(p.g[1], p.g[1]), G2 = bs_pk2(p.g[2], p.g[2]), G3 = bs_pk2(p.g[3], p.g[3]),
-                 G4 = bs_pk2(p.g[4], p.g[4]);
-    const bs_u64 BIAS = bs_pk2(kSepBias, kSepBias);
+    // vertical taps * 2^75 (the pixels enter as q * 2^-149), horizontal taps * 2^74, and the bias with the guard band's lower edge
+    // (a ulps of 2^-15, exact) riding in it: a channel is inside the band iff its fraction bits are below 2a, i.e.
+    // (bits << 17) < zthr, and the masked value of every other channel is floor(S~).  All scaled on the host (launch_blur_sep), so
+    // they reach the packed FMAs as scalar operands from the constant bank instead of occupying twenty registers.
+    const bs_u64 G0 = bs_pk2(p.sgv[0], p.sgv[0]), G1 = bs_pk2(p.sgv[1], p.sgv[1]), G2 = bs_pk2(p.sgv[2], p.sgv[2]), G3 = bs_pk2(p.sgv[3], p.sgv[3]),
+                 G4 = bs_pk2(p.sgv[4], p.sgv[4]);
+    const bs_u64 H0 = bs_pk2(p.sgh[0], p.sgh[0]), H1 = bs_pk2(p.sgh[1], p.sgh[1]), H2 = bs_pk2(p.sgh[2], p.sgh[2]), H3 = bs_pk2(p.sgh[3], p.sgh[3]),
+                 H4 = bs_pk2(p.sgh[4], p.sgh[4]);
+    const bs_u64 BIAS = bs_pk2(p.sbias, p.sbias);
 
     // Five vertical accumulators per pair, one per output row in flight (slot = output row mod 5, counted from the
     // first row of the segment); the row loop is unrolled by five so that every accumulator is updated in place
@@ -181,7 +185,7 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const __grid_constant__
         n1 = __ldg(pn1);
         // raw pixels into the ring (for the replay): ring slot = PH
         asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring + PH * 256u + 8u * lane), "r"(q0), "r"(q1) : "memory");
-        const bs_u64 Q[4] = {bs_cvt2(q0, 0x7440, 0x7441), bs_cvt2(q0, 0x7442, 0x7443), bs_cvt2(q1, 0x7440, 0x7441), bs_cvt2(q1, 0x7442, 0x7443)};
+        const bs_u64 Q[4] = {bs_cvt2(q0, 0x4440, 0x4441), bs_cvt2(q0, 0x4442, 0x4443), bs_cvt2(q1, 0x4440, 0x4441), bs_cvt2(q1, 0x4442, 0x4443)};
         bs_u64 V[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -207,20 +211,24 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const __grid_constant__
             bs_u64 F[4];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                F[h] = bs_fma2(G4, R[h], bs_fma2(G3, V[2 + h], bs_fma2(G2, V[h], bs_fma2(G1, L[2 + h], bs_fma2(G0, L[h], BIAS)))));
+                F[h] = bs_fma2(H4, R[h], bs_fma2(H3, V[2 + h], bs_fma2(H2, V[h], bs_fma2(H1, L[2 + h], bs_fma2(H0, L[h], BIAS)))));
                 // pixel x0 + 1: taps x0-1 (L px1), x0 (own px0), x0+1 (own px1), x0+2 (R px0), x0+3 (R px1)
-                F[2 + h] = bs_fma2(G4, R[2 + h], bs_fma2(G3, R[h], bs_fma2(G2, V[2 + h], bs_fma2(G1, V[h], bs_fma2(G0, L[2 + h], BIAS)))));
+                F[2 + h] = bs_fma2(H4, R[2 + h], bs_fma2(H3, R[h], bs_fma2(H2, V[2 + h], bs_fma2(H1, V[h], bs_fma2(H0, L[2 + h], BIAS)))));
             }
             uint32_t z[8];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                z[2 * j] = (bs_lo(F[j]) << (32 - kSepFracBits)) + p.zoff;
-                z[2 * j + 1] = (bs_hi(F[j]) << (32 - kSepFracBits)) + p.zoff;
+                z[2 * j] = bs_lo(F[j]) << (32 - kSepFracBits);
+                z[2 * j + 1] = bs_hi(F[j]) << (32 - kSepFracBits);
             }
             const uint32_t zm0 = min(__vimin3_u32(z[0], z[1], z[2]), z[3]), zm1 = min(__vimin3_u32(z[4], z[5], z[6]), z[7]);
             uint32_t o0 = bs_pack(F[0], F[1]), o1 = bs_pack(F[2], F[3]);
             if (min(zm0, zm1) < p.zthr && store0) {   // lane-local fix (rare on textured content), only for pixels that are stored
-                const uint3 o = bs_fix(ring, (uint32_t)PH, lane, store1, F[0], F[1], F[2], F[3], p, o0, o1);
+                uint32_t fm = 0;   // (the bias carries the band's lower edge: inside iff the shifted fraction bits are below zthr)
+#pragma unroll
+                for (int k = 0; k < 8; k++) fm |= (z[k] < p.zthr ? 1u : 0u) << k;
+                if (!store1) fm &= 0xfu;
+                const uint3 o = bs_fix(ring, (uint32_t)PH, lane, fm, p.flat, o0, o1);
                 o0 = (o.z & 1u) ? bs_replay(ring, (uint32_t)PH, 2u * lane, wts, p.slow_counter) : o.x;
                 o1 = (o.z & 2u) ? bs_replay(ring, (uint32_t)PH, 2u * lane + 1u, wts, p.slow_counter) : o.y;
             }

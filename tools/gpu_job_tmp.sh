@@ -1,6 +1,9 @@
 #!/bin/bash
-for lib in default tools/ab/*.so; do
+python -m pytest tests -m gpu -x -q -k "blur or gauss" 2>&1 | tail -n 3
+for rep in 1 2; do
+for lib in default tools/ab/head.so; do
   echo "== $lib"
   if [ $lib != default ]; then export RIP_LIB_PATH=$PWD/$lib; else unset RIP_LIB_PATH; fi
-  RIP_FUSED_NPX=4 python tools/prof_fused.py --frames 32 --launches 8
+  for c in noise alpha255; do python tools/prof_blur.py 5 1.0 16 6 $c; done
+done
 done
