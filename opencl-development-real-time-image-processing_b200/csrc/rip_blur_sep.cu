@@ -42,6 +42,7 @@ struct SepParams {
     uint32_t zoff, zthr;        // replay iff ((bits << 17) + zoff) < zthr
     float g[RIP_MAX_KSIZE];     // separable taps
     float sgv[5], sgh[5], sbias;   // streaming 5x5 kernel: vertical taps * 2^75, horizontal taps * 2^74, bias 256 + a * 2^-15
+    float rw[25];               // streaming 5x5 kernel: the reference's 25 weights * 2^100 (replay on integer bit patterns, bs_replay1)
     uint8_t flat[256];          // flat[v] = the reference's result for a CONSTANT KxK window of value v (its own sequence, host-evaluated)
     unsigned long long *slow_counter;   // optional statistics (NULL in production)
 };
@@ -383,17 +384,25 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
     const uint32_t a = (uint32_t)std::ceil(band / ulp + 0.5);
     p.zoff = a << (32 - kSepFracBits);
     p.zthr = (2u * a) << (32 - kSepFracBits);
+    bool stream_ok = ksize == 5;
     if (ksize == 5) {
         for (int k = 0; k < 5; k++) {
             p.sgv[k] = std::ldexp(p.g[k], 75);
             p.sgh[k] = std::ldexp(p.g[k], 74);
         }
         p.sbias = (float)(256.0 + a * ulp);
+        // the streaming kernel's replay multiplies the pixel's integer bit pattern (q * 2^-149) by w * 2^100: the product q w 2^-49
+        // carries the reference's mantissa iff it is a normal float, i.e. for weights that are 0 or >= 2^-70 (any Gaussian with
+        // sigma >= 0.3); anything else takes the tiled kernel
+        for (int i = 0; i < 25; i++) {
+            if (wts.w[i] != 0.0f && wts.w[i] < std::ldexp(1.0f, -70)) stream_ok = false;
+            p.rw[i] = std::ldexp(wts.w[i], 100);
+        }
     }
     // 5x5 RGBA: the streaming kernel for large inputs (1.4x the tiled kernel on 16 1080p frames), the tiled one for
     // small ones, where a block per 32x32 tile exposes more parallelism (one 683x1023 frame: 25 us against 31 us)
     const bool big = (long long)n_frames * out_rows * W >= (2LL << 20);
-    if (cn == 4 && ksize == 5 && !options().blur_tiled && (big || options().blur_stream)) {
+    if (cn == 4 && stream_ok && !options().blur_tiled && (big || options().blur_stream)) {
         // the streaming kernel: bands of 60 columns per warp, segments of rows sized so that the grid fills the GPU
         // (4 warm-up rows per segment)
         StreamGeo sg;
@@ -408,7 +417,7 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
         sg.n_segs = (out_rows + sg.seg_rows - 1) / sg.seg_rows;
         const long long blocks = (long long)n_frames * sg.n_segs * sg.n_band_groups;
         if (blocks > 0 && blocks <= 0x7fffffffLL) {
-            blur_stream5_kernel<<<(unsigned)blocks, kBsWarps * 32, 0, s>>>(p, wts, sg);
+            blur_stream5_kernel<<<(unsigned)blocks, kBsWarps * 32, 0, s>>>(p, sg);
             RIP_LAUNCH_CHECK();
             return RIP_OK;
         }

@@ -50,74 +50,118 @@ __device__ __forceinline__ uint32_t bs_pack(bs_u64 c01, bs_u64 c23)
     return __byte_perm(__byte_perm(bs_lo(t01), bs_hi(t01), 0x0040), __byte_perm(bs_lo(t23), bs_hi(t23), 0x0040), 0x5410);
 }
 
-// the reference's sequence for one pixel (GaussianBlur.cpp:236-258): column `col` of the warp's ring, rows oldest first
-__device__ __noinline__ uint32_t bs_replay(uint32_t ring, uint32_t cur_slot, uint32_t col, const Weights &wts, unsigned long long *slow_counter)
+// ---- cold path ---------------------------------------------------------------------------------------------------------
+// 0xff in every byte of the result whose byte of `d` is non-zero
+__device__ __forceinline__ uint32_t bs_nzb(uint32_t d)
 {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (uint32_t ky = 0; ky < 5u; ky++) {
-        uint32_t slot = cur_slot + 1u + ky;
-        slot = slot >= 5u ? slot - 5u : slot;
-        for (uint32_t kx = 0; kx < 5u; kx++) {
+    const uint32_t m = (d | ((d & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;   // the top bit of every non-zero byte
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(m));                    // (selector bit 3: replicate that bit over the byte)
+    return r;
+}
+// bits 0..3 -> 0xff in bytes 0..3
+__device__ __forceinline__ uint32_t bs_spread(uint32_t b4) { return ((b4 * 0x00204081u) & 0x01010101u) * 0xffu; }
+
+// The reference's value of ONE channel of one pixel (GaussianBlur.cpp:236-258: float accumulator from 0.0f, ky-major / kx-minor, one
+// rounded product and one rounded add per tap, clamp, truncate), from the warp's ring of raw pixels.  The isolated byte enters the
+// product as the denormal q * 2^-149 and the weights carry 2^100 (p.rw, scaled on the host; launch_blur_sep admits only weights
+// that are 0 or >= 2^-70, so every product and every partial sum is a normal float with the reference's mantissa): no I2F, and a
+// lane pays for the one channel that is inside the guard band, not for four (round 2 until here: four channels, 18 instructions per
+// tap, ~40 % of the kernel's executed instructions on noise).
+__device__ __forceinline__ uint32_t bs_replay1(uint32_t ring, uint32_t cur_slot, uint32_t col, uint32_t ch, const float *rw)
+{
+    const uint32_t sel = 0x4440u + ch;
+    float a = 0.f;
+    uint32_t slot = cur_slot;
+#pragma unroll 1
+    for (int ky = 0; ky < 5; ky++) {          // (rolled: the out-of-line fix must not raise the kernel's register count)
+        slot = slot == 4u ? 0u : slot + 1u;   // rows oldest first: (cur_slot + 1 + ky) mod 5
+        const uint32_t rb = ring + slot * 256u + 4u * col - 8u;
+#pragma unroll
+        for (int kx = 0; kx < 5; kx++) {
             uint32_t px;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(px) : "r"(ring + slot * 256u + 4u * (col + kx - 2u)));
-            const float w = wts.w[ky * 5u + kx];
-            a0 = __fadd_rn(a0, __fmul_rn((float)(px & 0xffu), w));
-            a1 = __fadd_rn(a1, __fmul_rn((float)((px >> 8) & 0xffu), w));
-            a2 = __fadd_rn(a2, __fmul_rn((float)((px >> 16) & 0xffu), w));
-            a3 = __fadd_rn(a3, __fmul_rn((float)(px >> 24), w));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(px) : "r"(rb + 4u * kx));
+            a = __fadd_rn(a, __fmul_rn(__uint_as_float(__byte_perm(px, 0u, sel)), rw[ky * 5 + kx]));
         }
     }
-    if (slow_counter) atomicAdd(slow_counter, 1ull);
-    return (uint32_t)__float2int_rz(fminf(fmaxf(a0, 0.f), 255.f)) | ((uint32_t)__float2int_rz(fminf(fmaxf(a1, 0.f), 255.f)) << 8) |
-           ((uint32_t)__float2int_rz(fminf(fmaxf(a2, 0.f), 255.f)) << 16) | ((uint32_t)__float2int_rz(fminf(fmaxf(a3, 0.f), 255.f)) << 24);
+    return (uint32_t)__float2int_rz(fminf(a * 562949953421312.0f /* 2^49 */, 255.f));   // (a >= 0: weights and pixels are)
 }
 
-// The fix of one lane-row, out of line: (1) which channels are constant over the 5 rows x 6 columns around the lane's two pixels?
-// Their result is flat[value] whatever the fast sum says -- the fast sum of a constant window sits on an integer, inside the guard
-// band, so the alpha channel of every real RGBA frame (255 throughout) and black or clipped regions flag every pixel.  (2) Only a
-// pixel with a flagged channel that is NOT constant runs the 25-tap replay.  Before round 2's end every flagged pixel ran the replay for its four channels:
-// 16 1080p frames with alpha = 255 took 977 us against 219 us for frames whose alpha is noise.
-// Returns the patched outputs in .x / .y and in .z which pixels still need the replay (bit 0 / bit 1); the caller runs it, so that
-// the call depth -- and with it the kernel's register allocation -- stays what it was.
-__device__ __noinline__ uint3 bs_fix(uint32_t ring, uint32_t cur_slot, uint32_t lane, uint32_t fm /* flagged channels: bits 0-3 pixel 0, bits 4-7 pixel 1 */,
-                                     const uint8_t *flat, uint32_t o0, uint32_t o1)
+// The fix of one lane-row, out of line.  fm: the channels inside the guard band (bits 0-3 pixel 0, bits 4-7 pixel 1).
+//  (1) A channel that is CONSTANT over the 5 rows x 6 columns around the lane's two pixels takes flat[value], the reference's own
+//      sequence for a constant window evaluated on the host: the fast sum of a constant window sits on an integer, inside the guard
+//      band, so the alpha channel of every real RGBA frame (255 throughout) and black or clipped regions flag every pixel.  The lane
+//      keeps {value word, constant-channel mask, row, exact bytes} of its last visit in shared memory: inside a constant region the
+//      next row only has to check the ONE new ring row against the remembered value (3 loads instead of 15); anything else -- first
+//      visit, a flagged channel that is not in the remembered mask -- runs the full check, which stops at the first row that shows
+//      every flagged channel to vary (noise: always the first).
+//  (2) Every other flagged channel is replayed, one (pixel, channel) per trip, all flagged lanes of the warp side by side.
+__device__ __noinline__ uint2 bs_fix(uint32_t ring, uint32_t hist, uint32_t cur_slot, uint32_t row, uint32_t lane, uint32_t fm, const SepParams &p,
+                                     uint32_t o0, uint32_t o1)
 {
     const uint32_t a0 = ring + 8u * lane - 8u;   // columns 2 lane - 2 .. 2 lane + 3 of a ring row (lanes 1..30: inside the row)
-    uint32_t ref, diff = 0;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ref) : "r"(a0 + cur_slot * 256u + 8u));
-#pragma unroll 1
-    for (uint32_t sl = 0; sl < 5u; sl++) {   // (rolled: the function must not raise the kernel's register count)
-        uint32_t w[6];
+    const uint32_t ha = hist + 16u * lane;
+    uint32_t ref, cm, hrow, cex;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ref), "=r"(cm), "=r"(hrow), "=r"(cex) : "r"(ha));
+    const uint32_t fcb = bs_spread((fm | (fm >> 4)) & 0xfu);
+    uint32_t w[6];
 #pragma unroll
-        for (int k = 0; k < 3; k++) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[2 * k]), "=r"(w[2 * k + 1]) : "r"(a0 + sl * 256u + 8u * k));
+    for (int k = 0; k < 3; k++) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[2 * k]), "=r"(w[2 * k + 1]) : "r"(a0 + cur_slot * 256u + 8u * k));
+    bool known = false;
+    if (hrow + 1u == row) {   // visited at the previous row: the window lost its oldest row and gained the newest
+        uint32_t d = 0;
 #pragma unroll
-        for (int k = 0; k < 6; k++) diff |= w[k] ^ ref;
+        for (int k = 0; k < 6; k++) d |= w[k] ^ ref;
+        cm &= ~bs_nzb(d);
+        known = (fcb & ~cm) == 0u;   // (a flagged channel outside the mask may have BECOME constant: full check)
     }
-    uint32_t cb = 0, cexact = 0, cbits = 0;   // 0xff per constant channel, those channels' exact bytes, one bit per constant channel
+    if (!known) {
+        ref = w[2];
+        uint32_t d = 0, slot = cur_slot, left = 4;
 #pragma unroll
-    for (int c = 0; c < 4; c++)
-        if (((diff >> (8 * c)) & 0xffu) == 0u) {
-            cb |= 0xffu << (8 * c);
-            cbits |= 1u << c;
-            cexact |= (uint32_t)flat[(ref >> (8 * c)) & 0xffu] << (8 * c);
+        for (int k = 0; k < 6; k++) d |= w[k] ^ ref;
+#pragma unroll 1
+        for (; left && (fcb & ~bs_nzb(d)); left--) {
+            slot = slot ? slot - 1u : 4u;
+#pragma unroll
+            for (int k = 0; k < 3; k++) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[2 * k]), "=r"(w[2 * k + 1]) : "r"(a0 + slot * 256u + 8u * k));
+#pragma unroll
+            for (int k = 0; k < 6; k++) d |= w[k] ^ ref;
         }
-    uint32_t need = 0;
-    if (fm & 0xfu & ~cbits) need |= 1u;
-    else if (fm & 0xfu) o0 = (o0 & ~cb) | cexact;
-    if ((fm >> 4) & ~cbits) need |= 2u;
-    else if (fm >> 4) o1 = (o1 & ~cb) | cexact;
-    return make_uint3(o0, o1, need);
+        cm = left ? 0u : ~bs_nzb(d);   // (stopped early: the other channels were not checked over all five rows)
+        cex = 0;
+        if (cm) cex = (uint32_t)p.flat[ref & 0xffu] | ((uint32_t)p.flat[(ref >> 8) & 0xffu] << 8) | ((uint32_t)p.flat[(ref >> 16) & 0xffu] << 16) |
+                      ((uint32_t)p.flat[ref >> 24] << 24);
+    }
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ha), "r"(ref), "r"(cm), "r"(row), "r"(cex) : "memory");
+    const uint32_t m0 = bs_spread(fm & 0xfu) & cm, m1 = bs_spread(fm >> 4) & cm;
+    o0 = (o0 & ~m0) | (cex & m0);
+    o1 = (o1 & ~m1) | (cex & m1);
+    const uint32_t cbits = ((cm & 0x01010101u) * 0x10204080u) >> 28;
+    uint32_t rem = fm & ~(cbits | (cbits << 4));
+    if (rem && p.slow_counter) atomicAdd(p.slow_counter, (unsigned long long)(((rem & 0xfu) != 0u) + ((rem >> 4) != 0u)));
+#pragma unroll 1
+    while (rem) {
+        const uint32_t i = (uint32_t)__ffs((int)rem) - 1u, ch = i & 3u;
+        rem &= rem - 1u;
+        const uint32_t v = bs_replay1(ring, cur_slot, 2u * lane + (i >> 2), ch, p.rw);
+        const uint32_t sel = 0x3210u ^ ((4u ^ ch) << (4u * ch));   // byte `ch` of the result <- v
+        if (i & 4u) o1 = __byte_perm(o1, v, sel);
+        else o0 = __byte_perm(o0, v, sel);
+    }
+    return make_uint2(o0, o1);
 }
 
 struct StreamGeo {
     int seg_rows, n_segs, n_band_groups;
 };
 
-__global__ void __launch_bounds__(kBsWarps * 32)
-blur_stream5_kernel(const __grid_constant__ SepParams p, const __grid_constant__ Weights wts, const StreamGeo sg)
+__global__ void __launch_bounds__(kBsWarps * 32, 5)
+blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
 {
-    __shared__ __align__(16) uint32_t ring_s[kBsWarps][5][64];        // raw pixels of the last 5 rows, per warp
-    __shared__ __align__(16) uint32_t vrow_s[kBsWarps][2][kBsRowB / 4];  // completed vertical sums, double-buffered
+    __shared__ __align__(16) uint32_t ring_s[kBsWarps][5][64];     // raw pixels of the last 5 rows, per warp
+    __shared__ __align__(16) uint32_t vrow_s[kBsWarps][34 * 8];    // the completed vertical sums of one row: 32 lanes x 4 pairs, one pad lane on either side
+    __shared__ __align__(16) uint32_t hist_s[kBsWarps][32 * 4];    // per lane: what the last visit of the cold path found (bs_fix)
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     int bid = blockIdx.x;
@@ -136,7 +180,14 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const __grid_constant__
     const bool store0 = lane >= 1u && lane <= 30u && x0 < p.W, store1 = lane >= 1u && lane <= 30u && x0 + 1 < p.W;
 
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(&ring_s[warp][0][0]);
-    const uint32_t vrow = (uint32_t)__cvta_generic_to_shared(&vrow_s[warp][0][0]);
+    const uint32_t hist = (uint32_t)__cvta_generic_to_shared(&hist_s[warp][0]);
+    // The two shared-memory addresses of the hot path, kept in registers: ptxas otherwise re-derives each of them from the thread index
+    // in every row (S2R, shifts, LEA: ~20 of the ~140 instructions of a row).  The neighbours' pairs sit at fixed offsets -32 / +32 from
+    // the lane's own: lanes 0 and 31 read the pad entries, and their results are never stored.
+    uint32_t ring_lane = ring + 8u * lane;
+    uint32_t vo = (uint32_t)__cvta_generic_to_shared(&vrow_s[warp][0]) + 32u + 32u * lane;
+    asm volatile("" : "+r"(ring_lane), "+r"(vo));
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %2, %1};" ::"r"(hist + 16u * lane), "r"(0u), "r"(0x7fffffffu) : "memory");
     // vertical taps * 2^75 (the pixels enter as q * 2^-149), horizontal taps * 2^74, and the bias with the guard band's lower edge
     // (a ulps of 2^-15, exact) riding in it: a channel is inside the band iff its fraction bits are below 2a, i.e.
     // (bits << 17) < zthr, and the masked value of every other channel is floor(S~).  All scaled on the host (launch_blur_sep), so
@@ -168,23 +219,33 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const __grid_constant__
         pn0 = row + c0;
         pn1 = row + c1;
     }
-    uint32_t n0 = __ldg(pn0), n1 = __ldg(pn1);   // the row loaded one step ahead
-    uint32_t *orow = reinterpret_cast<uint32_t *>(fdst + (size_t)(ys - p.out_row0) * p.W * 4);
+    // rows are loaded TWO steps ahead (one step ahead, the first use of a loaded pixel held 40 % of the kernel's stall samples at
+    // four blocks per SM: a step is ~1000 cycles, about the latency of a DRAM access under load)
+    uint32_t n0 = __ldg(pn0), n1 = __ldg(pn1);
+    if ((uint32_t)(ys - 2 - row_lo) < row_span) {
+        pn0 += p.W;
+        pn1 += p.W;
+    }
+    uint32_t m0 = __ldg(pn0), m1 = __ldg(pn1);
+    uint32_t *po = reinterpret_cast<uint32_t *>(fdst + (size_t)(ys - p.out_row0) * p.W * 4) + x0;   // this lane's two outputs of the row in flight
 
     // one row: PH = (r - (ys - 2)) mod 5; an output row lives in the slot of the phase at which it completes.
     // Row r is tap 4 of output r-2 (slot PH: completes now), tap 3 of r-1 (slot PH+1), tap 2 of r (PH+2), tap 1 of
     // r+1 (PH+3) and tap 0 of r+2 (slot PH+4, which completed one step ago: restart it).
-    auto step = [&](auto ph_tag, int r) {
+    auto step = [&](auto ph_tag, auto out_tag, int r) {
         constexpr int PH = decltype(ph_tag)::value;
+        constexpr bool OUT = decltype(out_tag)::value;   // false: one of the four warm-up rows of the segment
         const uint32_t q0 = n0, q1 = n1;
-        if ((uint32_t)(r - row_lo) < row_span) {   // row r + 1 is a new row (not a clamped repeat of row r)
+        n0 = m0;
+        n1 = m1;
+        if ((uint32_t)(r + 1 - row_lo) < row_span) {   // row r + 2 is a new row (not a clamped repeat of row r + 1)
             pn0 += p.W;
             pn1 += p.W;
         }
-        n0 = __ldg(pn0);
-        n1 = __ldg(pn1);
+        m0 = __ldg(pn0);
+        m1 = __ldg(pn1);
         // raw pixels into the ring (for the replay): ring slot = PH
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring + PH * 256u + 8u * lane), "r"(q0), "r"(q1) : "memory");
+        asm volatile("st.shared.v2.u32 [%0+%1], {%2, %3};" ::"r"(ring_lane), "n"(PH * 256), "r"(q0), "r"(q1) : "memory");
         const bs_u64 Q[4] = {bs_cvt2(q0, 0x4440, 0x4441), bs_cvt2(q0, 0x4442, 0x4443), bs_cvt2(q1, 0x4440, 0x4441), bs_cvt2(q1, 0x4442, 0x4443)};
         bs_u64 V[4];
 #pragma unroll
@@ -195,18 +256,16 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const __grid_constant__
             acc[(PH + 3) % 5][j] = bs_fma2(G1, Q[j], acc[(PH + 3) % 5][j]);
             acc[(PH + 4) % 5][j] = bs_mul2(G0, Q[j]);   // (that slot completed one step ago and is free)
         }
-        const int y = r - 2;   // the output row this step completes
-        if (y >= ys) {         // warp-uniform
-            const uint32_t vb = vrow + (uint32_t)(r & 1) * kBsRowB;
-            asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(vb + 32u * lane), "l"(V[0]), "l"(V[1]) : "memory");
-            asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(vb + 32u * lane + 16u), "l"(V[2]), "l"(V[3]) : "memory");
+        if (OUT) {   // this step completes output row r - 2
+            // (one buffer is enough: the __syncwarp at the end of the previous step separates its loads from these stores)
+            asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(vo), "l"(V[0]), "l"(V[1]) : "memory");
+            asm volatile("st.shared.v2.b64 [%0+16], {%1, %2};" ::"r"(vo), "l"(V[2]), "l"(V[3]) : "memory");
             __syncwarp();
             bs_u64 L[4], R[4];   // the four pairs of the left / right neighbour lane
-            const uint32_t la = vb + 32u * ((lane + 31u) & 31u), ra = vb + 32u * ((lane + 1u) & 31u);
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(L[0]), "=l"(L[1]) : "r"(la));
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(L[2]), "=l"(L[3]) : "r"(la + 16u));
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(R[0]), "=l"(R[1]) : "r"(ra));
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(R[2]), "=l"(R[3]) : "r"(ra + 16u));
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+-32];" : "=l"(L[0]), "=l"(L[1]) : "r"(vo));
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+-16];" : "=l"(L[2]), "=l"(L[3]) : "r"(vo));
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+32];" : "=l"(R[0]), "=l"(R[1]) : "r"(vo));
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+48];" : "=l"(R[2]), "=l"(R[3]) : "r"(vo));
             // pixel x0: taps x0-2 (L px0), x0-1 (L px1), x0 (own px0), x0+1 (own px1), x0+2 (R px0); channel pairs h = 0, 1
             bs_u64 F[4];
 #pragma unroll
@@ -228,29 +287,36 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < 8; k++) fm |= (z[k] < p.zthr ? 1u : 0u) << k;
                 if (!store1) fm &= 0xfu;
-                const uint3 o = bs_fix(ring, (uint32_t)PH, lane, fm, p.flat, o0, o1);
-                o0 = (o.z & 1u) ? bs_replay(ring, (uint32_t)PH, 2u * lane, wts, p.slow_counter) : o.x;
-                o1 = (o.z & 2u) ? bs_replay(ring, (uint32_t)PH, 2u * lane + 1u, wts, p.slow_counter) : o.y;
+                const uint2 o = bs_fix(ring, hist, (uint32_t)PH, (uint32_t)r, lane, fm, p, o0, o1);
+                o0 = o.x;
+                o1 = o.y;
             }
-            __syncwarp();   // the next step overwrites the ring's oldest row, which a replay above may still be reading
-            if (store0) orow[x0] = o0;
-            if (store1) orow[x0 + 1] = o1;
-            orow += p.W;
+            __syncwarp();   // the next step overwrites the ring's oldest row and the row of vertical sums, which lanes may still be reading
+            if (store0) po[0] = o0;
+            if (store1) po[1] = o1;
+            po += p.W;
         }
     };
 
+    typedef std::true_type T_;
+    typedef std::false_type F_;
     int r = ys - 2;
+    step(std::integral_constant<int, 0>{}, F_{}, r);
+    step(std::integral_constant<int, 1>{}, F_{}, r + 1);
+    step(std::integral_constant<int, 2>{}, F_{}, r + 2);
+    step(std::integral_constant<int, 3>{}, F_{}, r + 3);
+    r += 4;
 #pragma unroll 1
     for (; r + 4 <= ye + 1; r += 5) {
-        step(std::integral_constant<int, 0>{}, r);
-        step(std::integral_constant<int, 1>{}, r + 1);
-        step(std::integral_constant<int, 2>{}, r + 2);
-        step(std::integral_constant<int, 3>{}, r + 3);
-        step(std::integral_constant<int, 4>{}, r + 4);
+        step(std::integral_constant<int, 4>{}, T_{}, r);
+        step(std::integral_constant<int, 0>{}, T_{}, r + 1);
+        step(std::integral_constant<int, 1>{}, T_{}, r + 2);
+        step(std::integral_constant<int, 2>{}, T_{}, r + 3);
+        step(std::integral_constant<int, 3>{}, T_{}, r + 4);
     }
-    // the last 0..4 rows of the segment (phases 0.. in order)
-    if (r <= ye + 1) step(std::integral_constant<int, 0>{}, r++);
-    if (r <= ye + 1) step(std::integral_constant<int, 1>{}, r++);
-    if (r <= ye + 1) step(std::integral_constant<int, 2>{}, r++);
-    if (r <= ye + 1) step(std::integral_constant<int, 3>{}, r++);
+    // the last 0..4 rows of the segment
+    if (r <= ye + 1) step(std::integral_constant<int, 4>{}, T_{}, r++);
+    if (r <= ye + 1) step(std::integral_constant<int, 0>{}, T_{}, r++);
+    if (r <= ye + 1) step(std::integral_constant<int, 1>{}, T_{}, r++);
+    if (r <= ye + 1) step(std::integral_constant<int, 2>{}, T_{}, r++);
 }

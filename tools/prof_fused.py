@@ -39,6 +39,14 @@ elif a.kind == "letterbox":   # 25 % black bars above and below textured content
 elif a.kind == "halfflat":    # half of the frame is a clipped (constant) region
     one = rng.integers(0, 256, (a.h, a.w, 3), dtype=np.uint8)
     one[:, : a.w // 2] = 255
+elif a.kind == "halfflat77":  # half of the frame is a constant mid-grey region
+    one = rng.integers(0, 256, (a.h, a.w, 3), dtype=np.uint8)
+    one[:, : a.w // 2] = 77
+elif a.kind == "halfflat_odd":  # the constant region ends inside a lane
+    one = rng.integers(0, 256, (a.h, a.w, 3), dtype=np.uint8)
+    one[:, : a.w // 2 + 13] = 255
+elif a.kind == "flat255":
+    one = np.full((a.h, a.w, 3), 255, np.uint8)
 else:
     one = np.full((a.h, a.w, 3), 77, np.uint8)
 if a.fmt == "gray":
