@@ -42,6 +42,7 @@ struct SepParams {
     uint32_t zoff, zthr;        // replay iff ((bits << 17) + zoff) < zthr
     float g[RIP_MAX_KSIZE];     // separable taps
     float sgv[5], sgh[5], sbias;   // streaming 5x5 kernel: vertical taps * 2^75, horizontal taps * 2^74, bias 256 + a * 2^-15
+    uint32_t f255, a255;        // streaming 5x5 kernel: the bit pattern of the fast sum of an all-255 window (0: test disabled) and flat[255] << 24
     float rw[25];               // streaming 5x5 kernel: the reference's 25 weights * 2^100 (replay on integer bit patterns, bs_replay1)
     uint8_t flat[256];          // flat[v] = the reference's result for a CONSTANT KxK window of value v (its own sequence, host-evaluated)
     unsigned long long *slow_counter;   // optional statistics (NULL in production)
@@ -333,6 +334,49 @@ static void plan_flat_bytes(const float *w, int K, uint8_t flat[256])
     }
 }
 
+// The alpha channel of every frame the reference uploads is 255 (cv::COLOR_BGR2RGBA, ProgramHandler.cpp:127 of RT/), so its window is
+// constant everywhere and its fast sum sits inside the guard band for every pixel.  The streaming kernel recognises that case from the
+// fast sum itself: every step of its two FMA chains is monotone in every pixel, so the sum F255 of an all-255 window is the largest
+// value the chain can produce, and F == F255 holds for NO other window iff lowering any single input by one step lowers the result.
+// That is checked here with the kernel's own operand values and operation order (vertical: fma(G4,q4, fma(G3,q3, fma(G2,q2,
+// fma(G1,q1, G0*q0)))) on the denormal bit patterns; horizontal on top of the bias); if it fails, f255 = 0 disables the shortcut.
+static void plan_stream_alpha(SepParams &p)
+{
+    auto den = [](uint32_t q) { float f; memcpy(&f, &q, 4); return f; };   // q * 2^-149
+    auto vsum = [&](const uint32_t q[5]) {
+        volatile float a = p.sgv[0] * den(q[0]);
+        for (int k = 1; k < 5; k++) a = std::fmaf(p.sgv[k], den(q[k]), a);
+        return (float)a;
+    };
+    auto hsum = [&](const float v[5]) {
+        volatile float a = p.sbias;
+        for (int k = 0; k < 5; k++) a = std::fmaf(p.sgh[k], v[k], a);
+        return (float)a;
+    };
+    p.f255 = 0;
+    p.a255 = (uint32_t)p.flat[255] << 24;
+    uint32_t q[5] = {255, 255, 255, 255, 255};
+    const float v255 = vsum(q);
+    float vsec = 0.0f;   // the largest vertical sum of a column that is not all 255
+    for (int k = 0; k < 5; k++) {
+        q[k] = 254;
+        const float v = vsum(q);
+        q[k] = 255;
+        if (!(v < v255)) return;
+        vsec = v > vsec ? v : vsec;
+    }
+    float v[5] = {v255, v255, v255, v255, v255};
+    const float f255 = hsum(v);
+    for (int k = 0; k < 5; k++) {
+        v[k] = vsec;
+        const float f = hsum(v);
+        v[k] = v255;
+        if (!(f < f255)) return;
+    }
+    if (!(f255 >= 256.0f && f255 < 512.0f)) return;
+    memcpy(&p.f255, &f255, 4);
+}
+
 template <int CN>
 static int launch_sep_cn(cudaStream_t s, const SepParams &p, const Weights &wts, dim3 grid, size_t smem)
 {
@@ -398,6 +442,7 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
             if (wts.w[i] != 0.0f && wts.w[i] < std::ldexp(1.0f, -70)) stream_ok = false;
             p.rw[i] = std::ldexp(wts.w[i], 100);
         }
+        plan_stream_alpha(p);
     }
     // 5x5 RGBA: the streaming kernel for large inputs (1.4x the tiled kernel on 16 1080p frames), the tiled one for
     // small ones, where a block per 32x32 tile exposes more parallelism (one 683x1023 frame: 25 us against 31 us)

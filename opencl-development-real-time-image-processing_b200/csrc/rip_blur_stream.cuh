@@ -280,8 +280,18 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
                 z[2 * j] = bs_lo(F[j]) << (32 - kSepFracBits);
                 z[2 * j + 1] = bs_hi(F[j]) << (32 - kSepFracBits);
             }
-            const uint32_t zm0 = min(__vimin3_u32(z[0], z[1], z[2]), z[3]), zm1 = min(__vimin3_u32(z[4], z[5], z[6]), z[7]);
             uint32_t o0 = bs_pack(F[0], F[1]), o1 = bs_pack(F[2], F[3]);
+            // alpha: a fast sum equal to that of an all-255 window proves the window IS all 255 (plan_stream_alpha): the exact result
+            // is flat[255] and the channel leaves the guard-band test -- the alpha channel of every frame the reference uploads
+            if (bs_hi(F[1]) == p.f255) {
+                z[3] = 0xffffffffu;
+                o0 = (o0 & 0x00ffffffu) | p.a255;
+            }
+            if (bs_hi(F[3]) == p.f255) {
+                z[7] = 0xffffffffu;
+                o1 = (o1 & 0x00ffffffu) | p.a255;
+            }
+            const uint32_t zm0 = min(__vimin3_u32(z[0], z[1], z[2]), z[3]), zm1 = min(__vimin3_u32(z[4], z[5], z[6]), z[7]);
             if (min(zm0, zm1) < p.zthr && store0) {   // lane-local fix (rare on textured content), only for pixels that are stored
                 uint32_t fm = 0;   // (the bias carries the band's lower edge: inside iff the shifted fraction bits are below zthr)
 #pragma unroll

@@ -205,6 +205,22 @@ def test_blur_constant_channels_take_the_table(ctx, oracle, k, sigma, stream, op
     _eq(ctx.process(g, rip.OP_GAUSSIAN, rip.FMT_GRAY8, ksize=k, weights=w), oracle.blur(g, k, weights=w, threads=0), f"constant regions, gray K={k}")
 
 
+@pytest.mark.parametrize("sigma", [1.0, 1.5, 0.6])
+def test_blur_streaming_alpha_255_shortcut_is_exact(ctx, oracle, sigma, opt):
+    """The streaming kernel takes alpha from the constant-window table when the fast sum equals that of an all-255 window (proved on
+    the host to identify the all-255 window).  Near misses -- 254 specks, 255 runs shorter than the window, image borders -- must not."""
+    opt("RIP_BLUR_STREAM", 1)
+    h, wd = 97, 246
+    rng = np.random.default_rng(77)
+    img = rng.integers(0, 256, (h, wd, 4), dtype=np.uint8)
+    img[..., 3] = 255
+    img[3::7, 5::11, 3] = 254                       # specks one level below
+    img[40:60, 100:180, 3] = rng.integers(253, 256, (20, 80), dtype=np.uint8)   # a region that hovers around 255
+    img[70:, :30, :3] = 255                         # clipped colour channels next to the border
+    w = rip.gauss_weights(5, sigma)
+    _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=5, weights=w), oracle.blur(img, 5, weights=w, threads=0), f"alpha shortcut sigma {sigma}")
+
+
 def test_blur_rejects_bad_arguments(ctx):
     img = np.zeros((8, 8, 4), np.uint8)
     with pytest.raises(rip.RipError):
