@@ -185,7 +185,7 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
     // in every row (S2R, shifts, LEA: ~20 of the ~140 instructions of a row).  The neighbours' pairs sit at fixed offsets -32 / +32 from
     // the lane's own: lanes 0 and 31 read the pad entries, and their results are never stored.
     uint32_t ring_lane = ring + 8u * lane;
-    uint32_t vo = (uint32_t)__cvta_generic_to_shared(&vrow_s[warp][0]) + 32u + 32u * lane;
+    uint32_t vo = (uint32_t)__cvta_generic_to_shared(&vrow_s[warp][0]) + 8u + 8u * lane;
     asm volatile("" : "+r"(ring_lane), "+r"(vo));
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %2, %1};" ::"r"(hist + 16u * lane), "r"(0u), "r"(0x7fffffffu) : "memory");
     // vertical taps * 2^75 (the pixels enter as q * 2^-149), horizontal taps * 2^74, and the bias with the guard band's lower edge
@@ -238,9 +238,10 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
         const uint32_t q0 = n0, q1 = n1;
         n0 = m0;
         n1 = m1;
-        if ((uint32_t)(r + 1 - row_lo) < row_span) {   // row r + 2 is a new row (not a clamped repeat of row r + 1)
-            pn0 += p.W;
-            pn1 += p.W;
+        {   // row r + 2 is a new row (not a clamped repeat of row r + 1) iff row_lo <= r + 1 < row_hi
+            const size_t adv = (uint32_t)(r + 1 - row_lo) < row_span ? (size_t)(uint32_t)p.W : (size_t)0;
+            pn0 += adv;
+            pn1 += adv;
         }
         m0 = __ldg(pn0);
         m1 = __ldg(pn1);
@@ -258,14 +259,15 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
         }
         if (OUT) {   // this step completes output row r - 2
             // (one buffer is enough: the __syncwarp at the end of the previous step separates its loads from these stores)
-            asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(vo), "l"(V[0]), "l"(V[1]) : "memory");
-            asm volatile("st.shared.v2.b64 [%0+16], {%1, %2};" ::"r"(vo), "l"(V[2]), "l"(V[3]) : "memory");
+#pragma unroll
+            for (int j = 0; j < 4; j++) asm volatile("st.shared.b64 [%0], %1;" ::"r"(vo + 272u * j), "l"(V[j]) : "memory");
             __syncwarp();
             bs_u64 L[4], R[4];   // the four pairs of the left / right neighbour lane
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+-32];" : "=l"(L[0]), "=l"(L[1]) : "r"(vo));
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+-16];" : "=l"(L[2]), "=l"(L[3]) : "r"(vo));
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+32];" : "=l"(R[0]), "=l"(R[1]) : "r"(vo));
-            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+48];" : "=l"(R[2]), "=l"(R[3]) : "r"(vo));
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(L[j]) : "r"(vo + 272u * j - 8u));
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(R[j]) : "r"(vo + 272u * j + 8u));
+            }
             // pixel x0: taps x0-2 (L px0), x0-1 (L px1), x0 (own px0), x0+1 (own px1), x0+2 (R px0); channel pairs h = 0, 1
             bs_u64 F[4];
 #pragma unroll

@@ -1,11 +1,9 @@
 #!/bin/bash
 python -m pytest tests -m gpu -x -q -k "blur or gauss" 2>&1 | tail -n 3
 for rep in 1 2; do
-for lib in default tools/ab/c1.so; do
+for lib in default tools/ab/*.so; do
   echo "== $lib"
   if [ $lib != default ]; then export RIP_LIB_PATH=$PWD/$lib; else unset RIP_LIB_PATH; fi
   for c in noise alpha255 sky; do python tools/prof_blur.py 5 1.0 16 8 $c; done
 done
 done
-unset RIP_LIB_PATH
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:blur_stream5 -s 1 -c 1 -o gpurun_out/r2q_blur5_alpha255 -f python tools/prof_blur.py 5 1.0 16 3 alpha255 > gpurun_out/r2q_ncu_blur5.log 2>&1
