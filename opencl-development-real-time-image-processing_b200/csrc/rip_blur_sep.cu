@@ -42,6 +42,7 @@ struct SepParams {
     uint32_t zoff, zthr;        // replay iff ((bits << 17) + zoff) < zthr
     float g[RIP_MAX_KSIZE];     // separable taps
     float sgv[5], sgh[5], sbias;   // streaming 5x5 kernel: vertical taps * 2^75, horizontal taps * 2^74, bias 256 + a * 2^-15
+    float sg1[RIP_MAX_KSIZE], sg2[RIP_MAX_KSIZE];   // streaming KxK kernel: first-pass taps * 2^75, second-pass taps * 2^74
     uint32_t f255, a255;        // streaming 5x5 kernel: the bit pattern of the fast sum of an all-255 window (0: test disabled) and flat[255] << 24
     float rw[25];               // streaming 5x5 kernel: the reference's 25 weights * 2^100 (replay on integer bit patterns, bs_replay1)
     uint8_t flat[256];          // flat[v] = the reference's result for a CONSTANT KxK window of value v (its own sequence, host-evaluated)
@@ -272,6 +273,7 @@ blur_sep_kernel(const __grid_constant__ SepParams p, const __grid_constant__ Wei
 }
 
 #include "rip_blur_stream.cuh"
+#include "rip_blur_streamk.cuh"
 
 unsigned long long *g_sep_slow_counter = nullptr;
 
@@ -428,6 +430,11 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
     const uint32_t a = (uint32_t)std::ceil(band / ulp + 0.5);
     p.zoff = a << (32 - kSepFracBits);
     p.zthr = (2u * a) << (32 - kSepFracBits);
+    for (int k = 0; k < ksize; k++) {
+        p.sg1[k] = std::ldexp(p.g[k], 75);
+        p.sg2[k] = std::ldexp(p.g[k], 74);
+    }
+    p.sbias = (float)(256.0 + a * ulp);
     bool stream_ok = ksize == 5;
     if (ksize == 5) {
         for (int k = 0; k < 5; k++) {
@@ -463,6 +470,45 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
         const long long blocks = (long long)n_frames * sg.n_segs * sg.n_band_groups;
         if (blocks > 0 && blocks <= 0x7fffffffLL) {
             blur_stream5_kernel<<<(unsigned)blocks, kBsWarps * 32, 0, s>>>(p, sg);
+            RIP_LAUNCH_CHECK();
+            return RIP_OK;
+        }
+    }
+    // 9x9 and 17x17 RGBA (the reference's default): the accumulate-form streaming kernel for large inputs
+    if (cn == 4 && (ksize == 9 || ksize == 17) && !options().blur_tiled && (big || options().blur_stream) && W <= 65536) {
+        bool ok = true;   // the replay multiplies integer bit patterns by w * 2^100: weights must be 0 or >= 2^-70 (see above)
+        Weights rws;
+        memset(&rws, 0, sizeof(rws));
+        for (int i = 0; i < ksize * ksize; i++) {
+            if (wts.w[i] != 0.0f && wts.w[i] < std::ldexp(1.0f, -70)) ok = false;
+            rws.w[i] = std::ldexp(wts.w[i], 100);
+        }
+        StreamGeo sg;
+        const int n_bands = (W + kSkBand - 1) / kSkBand;
+        sg.n_band_groups = (n_bands + kSkWarps - 1) / kSkWarps;
+        int device = 0;
+        cudaGetDevice(&device);
+        // rows per segment: every segment pays K - 1 warm-up rows, and the grid runs in waves of `resident` blocks: take the split
+        // with the smallest (number of waves) x (rows a block walks)
+        const long long resident = (long long)sm_count(device) * (ksize <= 9 ? 5 : 4), per_seg = (long long)n_frames * sg.n_band_groups;
+        long long best = -1;
+        int best_n = 1;
+        for (int n = 1; n <= 64 && (out_rows + n - 1) / n >= 2 * ksize; n++) {
+            // (between the two models "blocks flow through the SMs" and "whole waves": a sparse last wave runs faster, not for free)
+            const long long rows = (out_rows + n - 1) / n + ksize - 1, blocks_n = per_seg * n, waves = (blocks_n + resident - 1) / resident;
+            const long long cost = rows * (blocks_n + waves * resident);
+            if (best < 0 || cost < best) {
+                best = cost;
+                best_n = n;
+            }
+        }
+        sg.seg_rows = (out_rows + best_n - 1) / best_n;
+        if (sg.seg_rows > 8192) sg.seg_rows = 8192;   // (the list entries hold 14 bits of row offset)
+        sg.n_segs = (out_rows + sg.seg_rows - 1) / sg.seg_rows;
+        const long long blocks = (long long)n_frames * sg.n_segs * sg.n_band_groups;
+        if (ok && blocks > 0 && blocks <= 0x7fffffffLL) {
+            if (ksize == 9) blur_streamk_kernel<9><<<(unsigned)blocks, kSkWarps * 32, 0, s>>>(p, rws, sg);
+            else blur_streamk_kernel<17><<<(unsigned)blocks, kSkWarps * 32, 0, s>>>(p, rws, sg);
             RIP_LAUNCH_CHECK();
             return RIP_OK;
         }

@@ -221,6 +221,36 @@ def test_blur_streaming_alpha_255_shortcut_is_exact(ctx, oracle, sigma, opt):
     _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=5, weights=w), oracle.blur(img, 5, weights=w, threads=0), f"alpha shortcut sigma {sigma}")
 
 
+@pytest.mark.parametrize("k,sigma", [(9, 2.5), (17, 6.0), (17, 3.0)])
+@pytest.mark.parametrize("shape", [(2, 150, 250), (1, 67, 61), (3, 40, 33), (1, 300, 1000)])
+def test_blur_streaming_k_kernel(ctx, oracle, k, sigma, shape, opt):
+    """9x9 / 17x17 RGBA through the accumulate-form streaming kernel (forced on small inputs): noise, smooth content, real-frame
+    content (alpha 255, black sky, a clipped channel, a flat patch at the corner), ragged widths, batches."""
+    opt("RIP_BLUR_STREAM", 1)
+    n, h, wd = shape
+    w = rip.gauss_weights(k, sigma)
+    imgs = np.stack([synth_frame("uniform" if i % 2 == 0 else "smooth", h, wd, 90 + i, 4) for i in range(n)])
+    imgs[-1, ..., 3] = 255
+    imgs[-1, : h // 3, :, :3] = 0
+    imgs[-1, h // 3: h // 2, : wd // 2, 1] = 255
+    imgs[-1, -20:, -25:] = (13, 13, 13, 255)
+    got = ctx.process(imgs, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w)
+    for i in range(n):
+        _eq(got[i], oracle.blur(imgs[i], k, weights=w, threads=0), f"streaming {k}x{k} blur {shape} frame {i}")
+
+
+def test_blur_streaming_k_kernel_1080p_default(ctx, oracle):
+    """The reference's default blur (17x17, sigma 6) on 1080p frames takes the streaming kernel by size: several row segments per band."""
+    rng = np.random.default_rng(17)
+    imgs = rng.integers(0, 256, (2, 1080, 1920, 4), dtype=np.uint8)
+    imgs[1, ..., 3] = 255
+    imgs[1, 200:500, 300:900, :3] = 255
+    w = rip.gauss_weights(17, 6.0)
+    got = ctx.process(imgs, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=17, weights=w)
+    for i in range(2):
+        _eq(got[i], oracle.blur(imgs[i], 17, weights=w, threads=0), f"17x17 1080p frame {i}")
+
+
 def test_blur_rejects_bad_arguments(ctx):
     img = np.zeros((8, 8, 4), np.uint8)
     with pytest.raises(rip.RipError):
