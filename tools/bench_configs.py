@@ -71,7 +71,13 @@ big4 = rng.integers(0, 256, (16, 1080, 1920, 4), dtype=np.uint8)
 d_in, d_out = dev_buf(big4), rip.DeviceBuffer(big4.nbytes)
 w = rip.gauss_weights(5, 1.0)
 us, best = timed(lambda: rip.gauss_dev(d_in.ptr, d_out.ptr, 1920, 1080, 16, 4, 5, w), n=7)
-row("          exact Gaussian 5x5 on 1920x1080 RGBA, batch 16", us, best, 16 * 1920 * 1080, 8)
+row("          exact Gaussian 5x5 on 1920x1080 RGBA, batch 16, noise in all four channels", us, best, 16 * 1920 * 1080, 8)
+big4[..., 3] = 255   # what the reference uploads: cv::COLOR_BGR2RGBA frames, alpha = 255 throughout
+d_in.upload(big4)
+for k, s in ((5, 1.0), (9, 2.5), (17, 6.0)):
+    w = rip.gauss_weights(k, s)
+    us, best = timed(lambda: rip.gauss_dev(d_in.ptr, d_out.ptr, 1920, 1080, 16, 4, k, w), n=7)
+    row(f"          exact Gaussian {k}x{k} sigma {s} on 1920x1080 RGBA, batch 16, alpha = 255", us, best, 16 * 1920 * 1080, 8)
 # config 3: Sobel on 1080p RGB, batch 64
 big = rng.integers(0, 256, (64, 1080, 1920, 3), dtype=np.uint8)
 d_in, d_out = dev_buf(big), rip.DeviceBuffer(64 * 1080 * 1920)
