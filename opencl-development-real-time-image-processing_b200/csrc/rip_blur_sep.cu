@@ -404,56 +404,81 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
     if ((cn != 1 && cn != 4) || ksize < 3) return RIP_EUNSUPPORTED;
     if (options().blur_exact) return RIP_EUNSUPPORTED;   // (tests compare the two kernels)
     if (cn == 4 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u)) return RIP_EUNSUPPORTED;
+    // Everything that depends on the weights alone -- separable taps and the guard band (O(K^2) libm calls), the constant-window table
+    // (256 K^2 operations), the scaled taps and weights of the streaming kernels, the alpha shortcut's proof -- is planned once and kept
+    // for the next launch: a caller's weights rarely change, and for one small frame the planning cost more than the kernel (17x17 on a
+    // 680 x 1023 frame: 45 us per call against 30 us best).
+    struct Plan {
+        bool valid = false, ok = false, stream5_ok = false, streamk_ok = false;
+        int ksize = 0;
+        float w[RIP_MAX_TAPS];
+        SepParams p;
+        Weights rws;   // the weights * 2^100 (streaming KxK kernel)
+    };
+    static std::mutex mu;
+    static Plan plan;
     SepParams p;
-    memset(&p, 0, sizeof(p));
-    double band = 0.0;
-    if (!plan_sep_blur(wts.w, ksize, p.g, &band)) return RIP_EUNSUPPORTED;
-    p.src = src; p.dst = dst; p.W = W; p.H = H;
-    p.src_row0 = src_row0; p.src_rows = src_rows; p.out_row0 = out_row0; p.out_rows = out_rows; p.ksize = ksize;
-    p.slow_counter = g_sep_slow_counter;
-    {   // the table costs 256 K^2 host operations: keep the last one (a caller's weights rarely change between launches)
-        static std::mutex mu;
-        static int last_k = 0;
-        static float last_w[RIP_MAX_TAPS];
-        static uint8_t last_flat[256];
+    Weights rws;
+    bool stream_ok, streamk_ok;
+    {
         std::lock_guard<std::mutex> lk(mu);
-        if (last_k != ksize || memcmp(last_w, wts.w, sizeof(float) * ksize * ksize) != 0) {
-            plan_flat_bytes(wts.w, ksize, last_flat);
-            memcpy(last_w, wts.w, sizeof(float) * ksize * ksize);
-            last_k = ksize;
+        if (!plan.valid || plan.ksize != ksize || memcmp(plan.w, wts.w, sizeof(float) * ksize * ksize) != 0) {
+            plan.valid = true;
+            plan.ksize = ksize;
+            memcpy(plan.w, wts.w, sizeof(float) * ksize * ksize);
+            SepParams &q = plan.p;
+            memset(&q, 0, sizeof(q));
+            double band = 0.0;
+            plan.ok = plan_sep_blur(wts.w, ksize, q.g, &band);
+            if (plan.ok) {
+                q.ksize = ksize;
+                plan_flat_bytes(wts.w, ksize, q.flat);
+                // F = S~ + 256 is rounded to a multiple of ulp = 2^-15 (error <= ulp/2): a pixel whose 15 fraction bits are
+                // >= a and <= 2^15 - 1 - a has S~ at least `band` away from every integer when a >= band / ulp + 1/2
+                const double ulp = std::ldexp(1.0, -kSepFracBits);
+                const uint32_t a = (uint32_t)std::ceil(band / ulp + 0.5);
+                q.zoff = a << (32 - kSepFracBits);
+                q.zthr = (2u * a) << (32 - kSepFracBits);
+                for (int k = 0; k < ksize; k++) {
+                    q.sg1[k] = std::ldexp(q.g[k], 75);
+                    q.sg2[k] = std::ldexp(q.g[k], 74);
+                }
+                q.sbias = (float)(256.0 + a * ulp);
+                // the streaming kernels' replay multiplies the pixel's integer bit pattern (q * 2^-149) by w * 2^100: the product
+                // q w 2^-49 carries the reference's mantissa iff it is a normal float, i.e. for weights that are 0 or >= 2^-70 (any
+                // Gaussian with sigma >= 0.3); anything else takes the tiled kernel
+                bool scaled_ok = true;
+                memset(&plan.rws, 0, sizeof(plan.rws));
+                for (int i = 0; i < ksize * ksize; i++) {
+                    if (wts.w[i] != 0.0f && wts.w[i] < std::ldexp(1.0f, -70)) scaled_ok = false;
+                    plan.rws.w[i] = std::ldexp(wts.w[i], 100);
+                }
+                plan.stream5_ok = ksize == 5 && scaled_ok;
+                plan.streamk_ok = (ksize == 9 || ksize == 17) && scaled_ok;
+                if (ksize == 5) {
+                    for (int k = 0; k < 5; k++) {
+                        q.sgv[k] = q.sg1[k];
+                        q.sgh[k] = q.sg2[k];
+                    }
+                    memcpy(q.rw, plan.rws.w, sizeof(q.rw));
+                    plan_stream_alpha(q);
+                }
+            }
         }
-        memcpy(p.flat, last_flat, 256);
+        if (!plan.ok) return RIP_EUNSUPPORTED;
+        p = plan.p;
+        stream_ok = plan.stream5_ok;
+        streamk_ok = plan.streamk_ok;
+        if (streamk_ok) rws = plan.rws;
     }
-    // F = S~ + 256 is rounded to a multiple of ulp = 2^-15 (error <= ulp/2): a pixel whose 15 fraction bits are
-    // >= a and <= 2^15 - 1 - a has S~ at least `band` away from every integer when a >= band / ulp + 1/2
-    const double ulp = std::ldexp(1.0, -kSepFracBits);
-    const uint32_t a = (uint32_t)std::ceil(band / ulp + 0.5);
-    p.zoff = a << (32 - kSepFracBits);
-    p.zthr = (2u * a) << (32 - kSepFracBits);
-    for (int k = 0; k < ksize; k++) {
-        p.sg1[k] = std::ldexp(p.g[k], 75);
-        p.sg2[k] = std::ldexp(p.g[k], 74);
-    }
-    p.sbias = (float)(256.0 + a * ulp);
-    bool stream_ok = ksize == 5;
-    if (ksize == 5) {
-        for (int k = 0; k < 5; k++) {
-            p.sgv[k] = std::ldexp(p.g[k], 75);
-            p.sgh[k] = std::ldexp(p.g[k], 74);
-        }
-        p.sbias = (float)(256.0 + a * ulp);
-        // the streaming kernel's replay multiplies the pixel's integer bit pattern (q * 2^-149) by w * 2^100: the product q w 2^-49
-        // carries the reference's mantissa iff it is a normal float, i.e. for weights that are 0 or >= 2^-70 (any Gaussian with
-        // sigma >= 0.3); anything else takes the tiled kernel
-        for (int i = 0; i < 25; i++) {
-            if (wts.w[i] != 0.0f && wts.w[i] < std::ldexp(1.0f, -70)) stream_ok = false;
-            p.rw[i] = std::ldexp(wts.w[i], 100);
-        }
-        plan_stream_alpha(p);
-    }
-    // 5x5 RGBA: the streaming kernel for large inputs (1.4x the tiled kernel on 16 1080p frames), the tiled one for
-    // small ones, where a block per 32x32 tile exposes more parallelism (one 683x1023 frame: 25 us against 31 us)
-    const bool big = (long long)n_frames * out_rows * W >= (2LL << 20);
+    p.src = src; p.dst = dst; p.W = W; p.H = H;
+    p.src_row0 = src_row0; p.src_rows = src_rows; p.out_row0 = out_row0; p.out_rows = out_rows;
+    p.slow_counter = g_sep_slow_counter;
+    // Which kernel (one frame, measured, tiled / streaming, us -- profiles/r2x_blur_small.txt): 5x5 on 640x512 33 / 25, 680x1023 27 / 23,
+    // 1080p 40 / 24, 4K 93 / 46; 9x9 on 1080p 44 / 44, 4K 125 / 87; 17x17 on 1080p 73 / 95, 4K 227 / 197.  The streaming kernels walk
+    // K - 1 warm-up rows per segment, so they need enough rows per warp to pay for them: from 0.3 Mpx for 5x5, 3 Mpx for 9x9, 6 Mpx for 17x17.
+    const long long n_px = (long long)n_frames * out_rows * W;
+    const bool big = n_px >= 300000LL;
     if (cn == 4 && stream_ok && !options().blur_tiled && (big || options().blur_stream)) {
         // the streaming kernel: bands of 60 columns per warp, segments of rows sized so that the grid fills the GPU
         // (4 warm-up rows per segment)
@@ -464,7 +489,7 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
         cudaGetDevice(&device);
         const long long want = (long long)sm_count(device) * 16;
         int seg = 128;
-        while (seg > 16 && (long long)n_frames * sg.n_band_groups * ((out_rows + seg - 1) / seg) < want) seg >>= 1;
+        while (seg > 8 && (long long)n_frames * sg.n_band_groups * ((out_rows + seg - 1) / seg) < want) seg >>= 1;
         sg.seg_rows = seg < out_rows ? seg : out_rows;
         sg.n_segs = (out_rows + sg.seg_rows - 1) / sg.seg_rows;
         const long long blocks = (long long)n_frames * sg.n_segs * sg.n_band_groups;
@@ -475,14 +500,7 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
         }
     }
     // 9x9 and 17x17 RGBA (the reference's default): the accumulate-form streaming kernel for large inputs
-    if (cn == 4 && (ksize == 9 || ksize == 17) && !options().blur_tiled && (big || options().blur_stream) && W <= 65536) {
-        bool ok = true;   // the replay multiplies integer bit patterns by w * 2^100: weights must be 0 or >= 2^-70 (see above)
-        Weights rws;
-        memset(&rws, 0, sizeof(rws));
-        for (int i = 0; i < ksize * ksize; i++) {
-            if (wts.w[i] != 0.0f && wts.w[i] < std::ldexp(1.0f, -70)) ok = false;
-            rws.w[i] = std::ldexp(wts.w[i], 100);
-        }
+    if (cn == 4 && streamk_ok && !options().blur_tiled && (n_px >= (ksize == 9 ? 3000000LL : 6000000LL) || options().blur_stream) && W <= 65536) {
         StreamGeo sg;
         const int n_bands = (W + kSkBand - 1) / kSkBand;
         sg.n_band_groups = (n_bands + kSkWarps - 1) / kSkWarps;
@@ -506,7 +524,7 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
         if (sg.seg_rows > 8192) sg.seg_rows = 8192;   // (the list entries hold 14 bits of row offset)
         sg.n_segs = (out_rows + sg.seg_rows - 1) / sg.seg_rows;
         const long long blocks = (long long)n_frames * sg.n_segs * sg.n_band_groups;
-        if (ok && blocks > 0 && blocks <= 0x7fffffffLL) {
+        if (blocks > 0 && blocks <= 0x7fffffffLL) {
             if (ksize == 9) blur_streamk_kernel<9><<<(unsigned)blocks, kSkWarps * 32, 0, s>>>(p, rws, sg);
             else blur_streamk_kernel<17><<<(unsigned)blocks, kSkWarps * 32, 0, s>>>(p, rws, sg);
             RIP_LAUNCH_CHECK();

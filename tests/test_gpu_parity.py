@@ -242,12 +242,12 @@ def test_blur_streaming_k_kernel(ctx, oracle, k, sigma, shape, opt):
 def test_blur_streaming_k_kernel_1080p_default(ctx, oracle):
     """The reference's default blur (17x17, sigma 6) on 1080p frames takes the streaming kernel by size: several row segments per band."""
     rng = np.random.default_rng(17)
-    imgs = rng.integers(0, 256, (2, 1080, 1920, 4), dtype=np.uint8)
-    imgs[1, ..., 3] = 255
+    imgs = rng.integers(0, 256, (3, 1080, 1920, 4), dtype=np.uint8)   # 6.2 Mpx: above the streaming kernel's threshold for 17x17
+    imgs[1:, ..., 3] = 255
     imgs[1, 200:500, 300:900, :3] = 255
     w = rip.gauss_weights(17, 6.0)
     got = ctx.process(imgs, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=17, weights=w)
-    for i in range(2):
+    for i in range(3):
         _eq(got[i], oracle.blur(imgs[i], 17, weights=w, threads=0), f"17x17 1080p frame {i}")
 
 
