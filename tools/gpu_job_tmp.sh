@@ -1,4 +1,9 @@
 #!/bin/bash
 timeout 600 python -m pytest tests -m gpu -x -q -k "blur or gauss" 2>&1 | tail -n 3
-python tools/prof_blur_small.py
-python tools/bench_configs.py 2>&1 | grep -i "gauss"
+for rep in 1 2; do
+for lib in default tools/ab/roll5.so tools/ab/base.so; do
+  echo "== $lib"
+  if [ $lib != default ]; then export RIP_LIB_PATH=$PWD/$lib; else unset RIP_LIB_PATH; fi
+  for c in noise alpha255 sky; do python tools/prof_blur.py 5 1.0 16 8 $c; done
+done
+done
