@@ -72,10 +72,10 @@ __device__ __forceinline__ uint32_t bs_replay1(uint32_t ring, uint32_t cur_slot,
 {
     const uint32_t sel = 0x4440u + ch;
     float a = 0.f;
-    uint32_t slot = cur_slot;
+    uint32_t slot = cur_slot >= 5u ? cur_slot - 5u : cur_slot + 5u;   // (the ring holds ten rows: the last five and the five being fetched)
 #pragma unroll 1
     for (int ky = 0; ky < 5; ky++) {          // (rolled: the out-of-line fix must not raise the kernel's register count)
-        slot = slot == 4u ? 0u : slot + 1u;   // rows oldest first: (cur_slot + 1 + ky) mod 5
+        slot = slot == 9u ? 0u : slot + 1u;   // rows oldest first: (cur_slot - 4 + ky) mod 10
         const uint32_t rb = ring + slot * 256u + 4u * col - 8u;
 #pragma unroll
         for (int kx = 0; kx < 5; kx++) {
@@ -122,7 +122,7 @@ __device__ __noinline__ uint2 bs_fix(uint32_t ring, uint32_t hist, uint32_t cur_
         for (int k = 0; k < 6; k++) d |= w[k] ^ ref;
 #pragma unroll 1
         for (; left && (fcb & ~bs_nzb(d)); left--) {
-            slot = slot ? slot - 1u : 4u;
+            slot = slot ? slot - 1u : 9u;
 #pragma unroll
             for (int k = 0; k < 3; k++) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[2 * k]), "=r"(w[2 * k + 1]) : "r"(a0 + slot * 256u + 8u * k));
 #pragma unroll
@@ -159,7 +159,7 @@ struct StreamGeo {
 __global__ void __launch_bounds__(kBsWarps * 32, 5)
 blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
 {
-    __shared__ __align__(16) uint32_t ring_s[kBsWarps][5][64];     // raw pixels of the last 5 rows, per warp
+    __shared__ __align__(16) uint32_t ring_s[kBsWarps][10][64];    // raw pixels per warp: the last five rows and the five rows being fetched (cp.async)
     __shared__ __align__(16) uint32_t vrow_s[kBsWarps][34 * 8];    // the completed vertical sums of one row: 32 lanes x 4 pairs, one pad lane on either side
     __shared__ __align__(16) uint32_t hist_s[kBsWarps][32 * 4];    // per lane: what the last visit of the cold path found (bs_fix)
 
@@ -219,14 +219,24 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
         pn0 = row + c0;
         pn1 = row + c1;
     }
-    // rows are loaded TWO steps ahead (one step ahead, the first use of a loaded pixel held 40 % of the kernel's stall samples at
-    // four blocks per SM: a step is ~1000 cycles, about the latency of a DRAM access under load)
-    uint32_t n0 = __ldg(pn0), n1 = __ldg(pn1);
-    if ((uint32_t)(ys - 2 - row_lo) < row_span) {
-        pn0 += p.W;
-        pn1 += p.W;
-    }
-    uint32_t m0 = __ldg(pn0), m1 = __ldg(pn1);
+    // Rows travel global -> shared ring with cp.async, FIVE rows ahead of their use (one commit group per row; a step waits until at
+    // most four groups are pending).  With register loads one or two rows ahead, the first use of a loaded pixel held 15-40 % of the
+    // kernel's stall samples in ONE of the five unrolled steps whatever the distance: a wait on a load's scoreboard also waits for
+    // every younger load that shares it.
+    uint32_t ringA = ring_lane, ringB = ring_lane + 5u * 256u;   // the half holding this trip's rows / the half being fetched
+    auto fetch = [&](uint32_t dst, int r_next) {   // issue row r_next (the pointers stand at row r_next - 1)
+        const size_t adv = (uint32_t)(r_next - 1 - row_lo) < row_span ? (size_t)(uint32_t)p.W : (size_t)0;
+        pn0 += adv;
+        pn1 += adv;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(pn0) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u), "l"(pn1) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ringA), "l"(pn0) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ringA + 4u), "l"(pn1) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+    for (int k = 1; k < 5; k++) fetch(ringA + 256u * k, ys - 2 + k);
     uint32_t *po = reinterpret_cast<uint32_t *>(fdst + (size_t)(ys - p.out_row0) * p.W * 4) + x0;   // this lane's two outputs of the row in flight
 
     // one row: PH = (r - (ys - 2)) mod 5; an output row lives in the slot of the phase at which it completes.
@@ -235,18 +245,10 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
     auto step = [&](auto ph_tag, auto out_tag, int r) {
         constexpr int PH = decltype(ph_tag)::value;
         constexpr bool OUT = decltype(out_tag)::value;   // false: one of the four warm-up rows of the segment
-        const uint32_t q0 = n0, q1 = n1;
-        n0 = m0;
-        n1 = m1;
-        {   // row r + 2 is a new row (not a clamped repeat of row r + 1) iff row_lo <= r + 1 < row_hi
-            const size_t adv = (uint32_t)(r + 1 - row_lo) < row_span ? (size_t)(uint32_t)p.W : (size_t)0;
-            pn0 += adv;
-            pn1 += adv;
-        }
-        m0 = __ldg(pn0);
-        m1 = __ldg(pn1);
-        // raw pixels into the ring (for the replay): ring slot = PH
-        asm volatile("st.shared.v2.u32 [%0+%1], {%2, %3};" ::"r"(ring_lane), "n"(PH * 256), "r"(q0), "r"(q1) : "memory");
+        uint32_t q0, q1;
+        asm volatile("cp.async.wait_group 4;" ::: "memory");
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(q0), "=r"(q1) : "r"(ringA + PH * 256u) : "memory");
+        fetch(ringB + PH * 256u, r + 5);
         const bs_u64 Q[4] = {bs_cvt2(q0, 0x4440, 0x4441), bs_cvt2(q0, 0x4442, 0x4443), bs_cvt2(q1, 0x4440, 0x4441), bs_cvt2(q1, 0x4442, 0x4443)};
         bs_u64 V[4];
 #pragma unroll
@@ -299,7 +301,7 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
 #pragma unroll
                 for (int k = 0; k < 8; k++) fm |= (z[k] < p.zthr ? 1u : 0u) << k;
                 if (!store1) fm &= 0xfu;
-                const uint2 o = bs_fix(ring, hist, (uint32_t)PH, (uint32_t)r, lane, fm, p, o0, o1);
+                const uint2 o = bs_fix(ring, hist, (uint32_t)PH + (ringA != ring_lane ? 5u : 0u), (uint32_t)r, lane, fm, p, o0, o1);
                 o0 = o.x;
                 o1 = o.y;
             }
@@ -312,6 +314,11 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
 
     typedef std::true_type T_;
     typedef std::false_type F_;
+    auto swap_halves = [&]() {
+        const uint32_t t = ringA;
+        ringA = ringB;
+        ringB = t;
+    };
     int r = ys - 2;
     step(std::integral_constant<int, 0>{}, F_{}, r);
     step(std::integral_constant<int, 1>{}, F_{}, r + 1);
@@ -321,14 +328,19 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
 #pragma unroll 1
     for (; r + 4 <= ye + 1; r += 5) {
         step(std::integral_constant<int, 4>{}, T_{}, r);
+        swap_halves();
         step(std::integral_constant<int, 0>{}, T_{}, r + 1);
         step(std::integral_constant<int, 1>{}, T_{}, r + 2);
         step(std::integral_constant<int, 2>{}, T_{}, r + 3);
         step(std::integral_constant<int, 3>{}, T_{}, r + 4);
     }
     // the last 0..4 rows of the segment
-    if (r <= ye + 1) step(std::integral_constant<int, 4>{}, T_{}, r++);
+    if (r <= ye + 1) {
+        step(std::integral_constant<int, 4>{}, T_{}, r++);
+        swap_halves();
+    }
     if (r <= ye + 1) step(std::integral_constant<int, 0>{}, T_{}, r++);
     if (r <= ye + 1) step(std::integral_constant<int, 1>{}, T_{}, r++);
     if (r <= ye + 1) step(std::integral_constant<int, 2>{}, T_{}, r++);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // (rows fetched past the segment's end)
 }

@@ -1,7 +1,7 @@
 #!/bin/bash
 timeout 600 python -m pytest tests -m gpu -x -q -k "blur or gauss" 2>&1 | tail -n 3
 for rep in 1 2; do
-for lib in default tools/ab/roll5.so tools/ab/base.so; do
+for lib in default tools/ab/base.so; do
   echo "== $lib"
   if [ $lib != default ]; then export RIP_LIB_PATH=$PWD/$lib; else unset RIP_LIB_PATH; fi
   for c in noise alpha255 sky; do python tools/prof_blur.py 5 1.0 16 8 $c; done
