@@ -274,6 +274,63 @@ __device__ __forceinline__ void load_row_x2(RawX<NPX, CN> &r, const uint8_t *p)
     }
 }
 
+// RIP_X3_CPASYNC = 1 (the default): input rows travel global -> shared with cp.async, NB rows ahead of their use (one commit
+// group per row, the step of row r waits until at most NB - 1 groups are pending), and each lane reads its own bytes back with
+// LDS.  0: register loads NB rows ahead (rounds 1-2).  With register loads the first consumer of a loaded row in ONE of the
+// unrolled steps held 8.5 % of the kernel's stall samples (profiles/r2m_fused_x3_hotspots.txt) whatever the distance -- a wait
+// on a load's scoreboard also waits for every younger load that shares it (seen and fixed first in the streaming blur,
+// rip_blur_stream.cuh) -- and the three row buffers occupied 18 registers.
+#ifndef RIP_X3_CPASYNC
+#define RIP_X3_CPASYNC 1
+#endif
+
+// this lane's NW words of a row: global -> shared (asynchronous), shared -> registers
+template <int NPX, int CN>
+__device__ __forceinline__ void cp_row_x3(uint32_t dst, const uint8_t *p)
+{
+    constexpr int NW = NPX * CN / 4;
+    if constexpr (NW == 1) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(p) : "memory");
+    } else if constexpr (NW == 2) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p) : "memory");
+    } else if constexpr (NW == 3) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * k), "l"(p + 4 * k) : "memory");
+    } else if constexpr (NW == 4) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p) : "memory");
+    } else if constexpr (NW == 6) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * k), "l"(p + 8 * k) : "memory");
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2; k++) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * k), "l"(p + 16 * k) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int NPX, int CN>
+__device__ __forceinline__ void lds_row_x3(RawX<NPX, CN> &r, uint32_t a)
+{
+    constexpr int NW = NPX * CN / 4;
+    if constexpr (NW == 1) {
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r.w[0]) : "r"(a) : "memory");
+    } else if constexpr (NW == 2) {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[1]) : "r"(a) : "memory");
+    } else if constexpr (NW == 3) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r.w[k]) : "r"(a + 4u * k) : "memory");
+    } else if constexpr (NW == 4) {
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "r"(a) : "memory");
+    } else if constexpr (NW == 6) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.w[2 * k]), "=r"(r.w[2 * k + 1]) : "r"(a + 8u * k) : "memory");
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.w[4 * k]), "=r"(r.w[4 * k + 1]), "=r"(r.w[4 * k + 2]), "=r"(r.w[4 * k + 3]) : "r"(a + 16u * k) : "memory");
+    }
+}
+
 // RIP_X3_ACC = 1 (the default): the vertical pass carries four rows of partial sums in registers (accumulate form, five
 // packed FMAs per pixel pair and row, no shared-memory reads on the hot path); 0: it re-reads gray rows r-1 .. r-4 from the
 // ring (eight LDS.128 per lane and row, 32 registers of state less).  Measured on 32 4K frames with the round's final cold
@@ -296,6 +353,7 @@ struct GeoX {
     uint32_t ring_lane;      // shared-memory byte address of this lane's 16 bytes in plane 0 of slot 0 of the warp's gray ring
     uint32_t ringA, ringB;   // main loop: ring_lane + the half (slots 0-2 / 3-5) this trip writes / wrote last trip
     uint32_t slot;           // head / tail rows: slot of the newest gray row
+    uint32_t raw_lane, rs;   // RIP_X3_CPASYNC: shared-memory byte address of this lane's bytes in slot 0 of the warp's raw-row ring; head / tail rows: slot of the row in use
     uint32_t in_pitch;
     int adv_lo, adv_n;       // the source pointer advances before the load of step r iff 0 <= r - adv_lo < adv_n
     uint32_t pf_off;         // byte offset from src of the line this lane prefetches into L2 (0: none)
@@ -442,9 +500,18 @@ __device__ RIP_REPLAY_FN uint32_t blur_replay_lane(uint32_t my, const uint32_t (
 //   EDGE     the warp's band holds image column 0 and/or W-1: per-lane border selects in x.
 //   KS       position of the row inside a main-loop trip (0, 1, 2): the ring slots of rows r .. r-4 are then compile-time
 //            offsets from the two half-ring bases geo.ringA / geo.ringB.  KS = -1 (head / tail rows): run-time slots.
-template <int NPX, int CN, bool BGR, bool BLUR, bool SPECIAL, bool EDGE, bool STATS, int KS>
+template <int NPX, int CN, bool BGR, bool BLUR, bool SPECIAL, bool EDGE, bool STATS, int KS, int NB>
+#if RIP_X3_CPASYNC
+__device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, const uint32_t raw_addr, const X2Params &xp, GeoX &geo, int r)
+#else
 __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, const X2Params &xp, GeoX &geo, int r)
+#endif
 {
+#if RIP_X3_CPASYNC
+    RawX<NPX, CN> buf;   // row r: fetched NB steps ago
+    asm volatile("cp.async.wait_group %0;" ::"n"(NB - 1) : "memory");
+    lds_row_x3<NPX, CN>(buf, raw_addr);
+#endif
     constexpr int NP = NPX / 2;
     constexpr int kRowB = 32 * NPX * 4;  // bytes per ring row
     static_assert(SPECIAL == (KS < 0), "head / tail rows use run-time ring slots");
@@ -500,7 +567,11 @@ __device__ __forceinline__ void step_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> &buf, 
         } else {
             geo.src += geo.in_pitch;   // (the main loop stops short of the rows where the band ends)
         }
+#if RIP_X3_CPASYNC
+        cp_row_x3<NPX, CN>(raw_addr, geo.src);   // row r + NB into the slot row r just left
+#else
         load_row_x2<NPX, CN>(buf, geo.src);
+#endif
 #if RIP_X2_L2PF > 0
         // pull the warp's bytes of a row further down into L2 (one 128-byte line per lane; pf_off is 0 in
         // the lanes that have no line to fetch and at the rows the band does not hold)
@@ -737,6 +808,59 @@ struct X2Cfg {
     static constexpr int NB = BLUR ? 3 : 6;
 };
 
+#if RIP_X3_CPASYNC
+template <int NPX, int CN, bool BGR, bool BLUR, bool EDGE, int NB, bool STATS>
+__device__ __forceinline__ void run_rows_x2(WarpX<NPX, CN> &st, const X2Params &xp, GeoX &geo, int r)
+{
+    constexpr uint32_t kRowB = 32 * NPX * 4;
+    constexpr uint32_t kRawB = 32 * NPX * CN;   // bytes of one raw row of the warp's band
+    const FusedParams &p = xp.f;
+    // head: up to the first storing row -- and, with the blur stage, until the newest gray row sits in the last slot of a
+    // half ring (slot 2 or 5), so that the main loop's trips write whole halves
+#pragma unroll 1
+    for (; (r <= geo.r_store || (BLUR && (geo.slot != 2u && geo.slot != 5u))) && r < geo.r_last; r++) {
+        step_x2<NPX, CN, BGR, BLUR, true, EDGE, STATS, -1, NB>(st, geo.raw_lane + geo.rs * kRawB, xp, geo, r);
+        geo.rs = geo.rs == (uint32_t)NB - 1u ? 0u : geo.rs + 1u;
+    }
+    const int r_main_last = min(geo.r_last - 1, p.in_row0 + p.in_rows - 1 - NB - RIP_X2_L2PF);
+    static_assert(!BLUR || NB == 3, "the half-ring addressing assumes three rows per trip");
+    if constexpr (BLUR) {
+        geo.ringA = geo.ring_lane + (geo.slot == 2u ? 3u * kRowB : 0u);
+        geo.ringB = geo.ring_lane + (geo.slot == 2u ? 0u : 3u * kRowB);
+    }
+    // the raw-row slots of the NB steps of a trip (a trip returns to the slot it started from)
+    uint32_t ra[NB];
+    {
+        uint32_t s = geo.rs;
+#pragma unroll
+        for (int k = 0; k < NB; k++) {
+            ra[k] = geo.raw_lane + s * kRawB;
+            s = s == (uint32_t)NB - 1u ? 0u : s + 1u;
+        }
+    }
+#pragma unroll 1
+    for (; r + NB - 1 <= r_main_last; r += NB) {
+        if constexpr (BLUR) {
+            step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 0, NB>(st, ra[0], xp, geo, r);
+            step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 1, NB>(st, ra[1], xp, geo, r + 1);
+            step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 2, NB>(st, ra[2], xp, geo, r + 2);
+            const uint32_t t = geo.ringA;   // the half just written becomes "last trip's"
+            geo.ringA = geo.ringB;
+            geo.ringB = t;
+        } else {
+#pragma unroll
+            for (int k = 0; k < NB; k++) step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 0, NB>(st, ra[k], xp, geo, r + k);
+        }
+    }
+    if constexpr (BLUR) geo.slot = (geo.ringB - geo.ring_lane) / kRowB + 2u;   // newest row: last slot of the half written last
+#pragma unroll 1
+    for (; r <= geo.r_last; r++) {
+        step_x2<NPX, CN, BGR, BLUR, true, EDGE, STATS, -1, NB>(st, geo.raw_lane + geo.rs * kRawB, xp, geo, r);
+        geo.rs = geo.rs == (uint32_t)NB - 1u ? 0u : geo.rs + 1u;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // (rows fetched past the segment's end)
+}
+#else
 template <int NPX, int CN, bool BGR, bool BLUR, bool EDGE, int NB, bool STATS>
 __device__ __forceinline__ void run_rows_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> (&b)[NB], const X2Params &xp, GeoX &geo, int r)
 {
@@ -748,7 +872,7 @@ __device__ __forceinline__ void run_rows_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> (&
     // was tried: ptxas made the whole kernel larger, 3328 instead of 3264 instructions.)
 #pragma unroll 1
     for (; (r <= geo.r_store || (BLUR && (geo.slot != 2u && geo.slot != 5u))) && r < geo.r_last; r++) {
-        step_x2<NPX, CN, BGR, BLUR, true, EDGE, STATS, -1>(st, b[0], xp, geo, r);
+        step_x2<NPX, CN, BGR, BLUR, true, EDGE, STATS, -1, NB>(st, b[0], xp, geo, r);
         const RawX<NPX, CN> t = b[0];
 #pragma unroll
         for (int k = 0; k + 1 < NB; k++) b[k] = b[k + 1];
@@ -766,27 +890,29 @@ __device__ __forceinline__ void run_rows_x2(WarpX<NPX, CN> &st, RawX<NPX, CN> (&
 #pragma unroll 1
     for (; r + NB - 1 <= r_main_last; r += NB) {
         if constexpr (BLUR) {
-            step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 0>(st, b[0], xp, geo, r);
-            step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 1>(st, b[1], xp, geo, r + 1);
-            step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 2>(st, b[2], xp, geo, r + 2);
+            step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 0, NB>(st, b[0], xp, geo, r);
+            step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 1, NB>(st, b[1], xp, geo, r + 1);
+            step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 2, NB>(st, b[2], xp, geo, r + 2);
             const uint32_t t = geo.ringA;   // the half just written becomes "last trip's"
             geo.ringA = geo.ringB;
             geo.ringB = t;
         } else {
 #pragma unroll
-            for (int k = 0; k < NB; k++) step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 0>(st, b[k], xp, geo, r + k);
+            for (int k = 0; k < NB; k++) step_x2<NPX, CN, BGR, BLUR, false, EDGE, STATS, 0, NB>(st, b[k], xp, geo, r + k);
         }
     }
     if constexpr (BLUR) geo.slot = (geo.ringB - geo.ring_lane) / kRowB + 2u;   // newest row: last slot of the half written last
 #pragma unroll 1
     for (; r <= geo.r_last; r++) {
-        step_x2<NPX, CN, BGR, BLUR, true, EDGE, STATS, -1>(st, b[0], xp, geo, r);
+        step_x2<NPX, CN, BGR, BLUR, true, EDGE, STATS, -1, NB>(st, b[0], xp, geo, r);
         const RawX<NPX, CN> t = b[0];
 #pragma unroll
         for (int k = 0; k + 1 < NB; k++) b[k] = b[k + 1];
         b[NB - 1] = t;
     }
 }
+
+#endif
 
 template <int NPX, int CN, bool BGR, bool BLUR, bool STATS = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, NPX == 8 ? ((BLUR || CN == 1) ? RIP_X2_MINB8 : RIP_X2_MINB8_NOBLUR) : RIP_X2_MINB4)
@@ -799,6 +925,10 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     const FusedParams &p = xp.f;
 
     __shared__ __align__(16) uint32_t ring[BLUR ? kWarpsPerBlock * kRing * kRowW : 4];
+#if RIP_X3_CPASYNC
+    constexpr int kRawW = 32 * NPX * CN / 4;   // words of one raw row of a warp's band
+    __shared__ __align__(16) uint32_t raw_ring[kWarpsPerBlock * X2Cfg<NPX, CN, BGR, BLUR>::NB * kRawW];
+#endif
     // no block-level barrier: the warps are independent from the first instruction on
 
     GeoX geo;
@@ -860,6 +990,16 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     int r = ys - HALO;
     const uint32_t xoff = in_img ? (uint32_t)x * CN : 0u;
     constexpr int NB = X2Cfg<NPX, CN, BGR, BLUR>::NB;
+#if RIP_X3_CPASYNC
+    geo.raw_lane = (uint32_t)__cvta_generic_to_shared(raw_ring + warp * NB * kRawW) + (uint32_t)(NPX * CN) * (uint32_t)geo.lane;
+    geo.rs = 0u;
+#pragma unroll
+    for (int k = 0; k < NB; k++) {   // rows r .. r + NB - 1 into slots 0 .. NB - 1
+        const int i = min(max(r + k - p.in_row0, 0), p.in_rows - 1);
+        geo.src = in_base + (size_t)i * geo.in_pitch + xoff;
+        cp_row_x3<NPX, CN>(geo.raw_lane + (uint32_t)k * (uint32_t)(kRawW * 4), geo.src);
+    }
+#else
     RawX<NPX, CN> b[NB];   // rows r .. r + NB - 1
 #pragma unroll
     for (int k = 0; k < NB; k++) {
@@ -867,6 +1007,7 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
         geo.src = in_base + (size_t)i * geo.in_pitch + xoff;
         load_row_x2<NPX, CN>(b[k], geo.src);
     }
+#endif
     // step r loads row r + NB = one past the row src points at: advance iff in_row0 <= r + NB - 1 < in_row0 + in_rows - 1
     geo.adv_lo = p.in_row0 - (NB - 1);
     geo.adv_n = p.in_rows - 1;
@@ -879,5 +1020,9 @@ fused_x2_kernel(const __grid_constant__ X2Params xp)
     // output row produced by the step of input row r is r - HALO
     geo.dst = p.out + (size_t)frame * p.out_rows * W + (ptrdiff_t)(r - HALO - p.out_row0) * W + x;
 
+#if RIP_X3_CPASYNC
+    run_rows_x2<NPX, CN, BGR, BLUR, true, NB, STATS>(st, xp, geo, r);
+#else
     run_rows_x2<NPX, CN, BGR, BLUR, true, NB, STATS>(st, b, xp, geo, r);
+#endif
 }
