@@ -1,14 +1,10 @@
 #!/bin/bash
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 5
+timeout 600 python -m pytest tests -m gpu -x -q -k "blur or gauss" 2>&1 | tail -n 3
 for rep in 1 2; do
 for lib in default tools/ab/base.so; do
   echo "== $lib"
   if [ $lib != default ]; then export RIP_LIB_PATH=$PWD/$lib; else unset RIP_LIB_PATH; fi
-  python tools/prof_fused.py --frames 32 --launches 8
-  python tools/prof_fused.py --frames 32 --launches 8 --fmt rgba
-  python tools/prof_fused.py --frames 32 --launches 8 --fmt gray
-  python tools/prof_fused.py --op sobel --frames 32 --launches 8
-  python tools/prof_fused.py --op sobel --frames 64 --w 1920 --h 1080 --launches 8
-  python tools/prof_fused.py --frames 32 --launches 6 --kind flat
+  for c in noise alpha255; do python tools/prof_blur.py 17 6.0 16 6 $c; done
+  for c in noise alpha255; do python tools/prof_blur.py 9 2.5 16 6 $c; done
 done
 done
