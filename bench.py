@@ -291,6 +291,22 @@ def config_rows(rip, dev, stream, peak) -> list:
         us = gpu_median_us(rip, lambda: rip.gauss_dev(d_i.ptr, d_o.ptr, w, h, 1, 4, k, wk, device=dev, stream=stream), dev, stream, n=21)
         add(f"2: Gaussian {k}x{k} sigma {s} on {w}x{h} RGBA, 1 frame", w * h, 8, us,
             cpu_time(lambda: O.blur(rgba, k, weights=wk, threads=1), 1.5, 5), cpu_time(lambda: O.blur(rgba, k, weights=wk, threads=cores), 1.0, 10))
+    # the same two kernels at throughput size: 16 x 1080p RGBA frames with alpha = 255 (what the reference uploads, cv::COLOR_BGR2RGBA)
+    nb, hb, wb = 16, 1080, 1920
+    oneb = rng.integers(0, 256, (hb, wb, 4), dtype=np.uint8)
+    oneb[..., 3] = 255
+    d_i = rip.DeviceBuffer(nb * oneb.nbytes, dev)
+    for i in range(nb):
+        d_i.upload(np.roll(oneb, 29 * i, axis=1), offset=i * oneb.nbytes)
+    d_o = rip.DeviceBuffer(nb * oneb.nbytes, dev)
+    for k, s in ((5, 1.0), (17, 6.0)):
+        wk = rip.gauss_weights(k, s)
+        us = gpu_median_us(rip, lambda: rip.gauss_dev(d_i.ptr, d_o.ptr, wb, hb, nb, 4, k, wk, device=dev, stream=stream), dev, stream, n=9)
+        t1 = cpu_time(lambda: O.blur(oneb[: hb // 8], k, weights=wk, threads=1), 1.0, 3) * 8
+        tn = cpu_time(lambda: O.blur(oneb, k, weights=wk, threads=cores), 1.0, 5)
+        add(f"2 (throughput): Gaussian {k}x{k} sigma {s} on {wb}x{hb} RGBA, alpha = 255, batch {nb}", nb * wb * hb, 8, us, t1 * nb, tn * nb,
+            {"oracle_sample": "1 of the 16 frames on all cores; 1/8 of its rows on one thread; scaled"})
+    d_i.free(); d_o.free()
     # config 3: Sobel on synthetic 1920x1080 RGB frames, batch 64
     n3, h, w = 64, 1080, 1920
     one = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)

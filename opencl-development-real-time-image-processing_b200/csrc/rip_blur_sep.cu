@@ -79,12 +79,14 @@ template <> struct SepPx<4> {
         return min(__vimin3_u32(a, b, c), d);
     }
     // the same with the channels in `cm` (0xff in the byte of a channel that is constant over the whole tile) left out
-    static __device__ __forceinline__ uint32_t zmin_masked(T f, uint32_t zoff, uint32_t cm)
+    // ... and a channel whose fast sum is below the band's width (bits < zlow = the bits of 256 + a ulps) left out as well: its true sum is
+    // >= 0 and below 1, the result is 0 either way (black sky: every all-zero window of a tile that is not constant sat on the replay list)
+    static __device__ __forceinline__ uint32_t zmin_masked(T f, uint32_t zoff, uint32_t cm, uint32_t zlow)
     {
-        const uint32_t a = ((__float_as_uint(f.x) << (32 - kSepFracBits)) + zoff) | (uint32_t)-(int)(cm & 1u);
-        const uint32_t b = ((__float_as_uint(f.y) << (32 - kSepFracBits)) + zoff) | (uint32_t)-(int)((cm >> 8) & 1u);
-        const uint32_t c = ((__float_as_uint(f.z) << (32 - kSepFracBits)) + zoff) | (uint32_t)-(int)((cm >> 16) & 1u);
-        const uint32_t d = ((__float_as_uint(f.w) << (32 - kSepFracBits)) + zoff) | (uint32_t)-(int)((cm >> 24) & 1u);
+        const uint32_t a = ((__float_as_uint(f.x) << (32 - kSepFracBits)) + zoff) | (uint32_t)-(int)(cm & 1u) | (__float_as_uint(f.x) < zlow ? ~0u : 0u);
+        const uint32_t b = ((__float_as_uint(f.y) << (32 - kSepFracBits)) + zoff) | (uint32_t)-(int)((cm >> 8) & 1u) | (__float_as_uint(f.y) < zlow ? ~0u : 0u);
+        const uint32_t c = ((__float_as_uint(f.z) << (32 - kSepFracBits)) + zoff) | (uint32_t)-(int)((cm >> 16) & 1u) | (__float_as_uint(f.z) < zlow ? ~0u : 0u);
+        const uint32_t d = ((__float_as_uint(f.w) << (32 - kSepFracBits)) + zoff) | (uint32_t)-(int)((cm >> 24) & 1u) | (__float_as_uint(f.w) < zlow ? ~0u : 0u);
         return min(__vimin3_u32(a, b, c), d);
     }
     static __device__ __forceinline__ uint32_t pack_fast(T f)   // floor(S~) of each channel: mantissa bits 15..22
@@ -111,7 +113,10 @@ template <> struct SepPx<1> {
     static __device__ __forceinline__ T mul(float g, T v) { return g * v; }
     static __device__ __forceinline__ T ref_step(T a, T v, float w) { return __fadd_rn(a, __fmul_rn(v, w)); }
     static __device__ __forceinline__ uint32_t zmin(T f, uint32_t zoff) { return (__float_as_uint(f) << (32 - kSepFracBits)) + zoff; }
-    static __device__ __forceinline__ uint32_t zmin_masked(T f, uint32_t zoff, uint32_t cm) { return zmin(f, zoff) | (uint32_t)-(int)(cm & 1u); }
+    static __device__ __forceinline__ uint32_t zmin_masked(T f, uint32_t zoff, uint32_t cm, uint32_t zlow)
+    {
+        return zmin(f, zoff) | (uint32_t)-(int)(cm & 1u) | (__float_as_uint(f) < zlow ? ~0u : 0u);
+    }
     static __device__ __forceinline__ uint32_t pack_fast(T f) { return (__float_as_uint(f) >> kSepFracBits) & 0xffu; }
     static __device__ __forceinline__ uint32_t pack_exact(T a) { return (uint32_t)__float2int_rz(fminf(fmaxf(a, 0.f), 255.f)); }
     static __device__ __forceinline__ void store(uint8_t *p, uint32_t v) { *p = (uint8_t)v; }
@@ -247,7 +252,7 @@ blur_sep_kernel(const __grid_constant__ SepParams p, const __grid_constant__ Wei
             const int oy = oy0 + j, y = y0 + oy;
             if (y < p.out_row0 + p.out_rows && y < p.H && x < p.W) {
                 P::store(fdst + ((size_t)(y - p.out_row0) * p.W + x) * CN, (P::pack_fast(f[j]) & ~cm) | cexact);
-                if (P::zmin_masked(f[j], p.zoff, cm) < p.zthr) list[atomicAdd(&n_list, 1u)] = (uint16_t)(oy << 5 | lane);
+                if (P::zmin_masked(f[j], p.zoff, cm, 0x43800000u + (p.zoff >> (32 - kSepFracBits))) < p.zthr) list[atomicAdd(&n_list, 1u)] = (uint16_t)(oy << 5 | lane);
             }
         }
     }

@@ -296,14 +296,19 @@ blur_stream5_kernel(const __grid_constant__ SepParams p, const StreamGeo sg)
                 o1 = (o1 & 0x00ffffffu) | p.a255;
             }
             const uint32_t zm0 = min(__vimin3_u32(z[0], z[1], z[2]), z[3]), zm1 = min(__vimin3_u32(z[4], z[5], z[6]), z[7]);
-            if (min(zm0, zm1) < p.zthr && store0) {   // lane-local fix (rare on textured content), only for pixels that are stored
+            // lane-local fix (rare on textured content), only for pixels that are stored.  A channel whose fast value is 0 needs none: the
+            // true sum is >= 0 and below 1 -- black sky (the reference's own Artemis_* images) costs one test: colour bytes all 0, alpha out
+            // of the band (or recognised as 255 above)
+            if (min(zm0, zm1) < p.zthr && store0 && !(((o0 | o1) & 0x00ffffffu) == 0u && min(z[3], z[7]) >= p.zthr)) {
                 uint32_t fm = 0;   // (the bias carries the band's lower edge: inside iff the shifted fraction bits are below zthr)
 #pragma unroll
-                for (int k = 0; k < 8; k++) fm |= (z[k] < p.zthr ? 1u : 0u) << k;
+                for (int k = 0; k < 8; k++) fm |= (z[k] < p.zthr && ((k < 4 ? o0 : o1) >> (8 * (k & 3)) & 0xffu) ? 1u : 0u) << k;
                 if (!store1) fm &= 0xfu;
-                const uint2 o = bs_fix(ring, hist, (uint32_t)PH + (ringA != ring_lane ? 5u : 0u), (uint32_t)r, lane, fm, p, o0, o1);
-                o0 = o.x;
-                o1 = o.y;
+                if (fm) {
+                    const uint2 o = bs_fix(ring, hist, (uint32_t)PH + (ringA != ring_lane ? 5u : 0u), (uint32_t)r, lane, fm, p, o0, o1);
+                    o0 = o.x;
+                    o1 = o.y;
+                }
             }
             __syncwarp();   // the next step overwrites the ring's oldest row and the row of vertical sums, which lanes may still be reading
             if (store0) po[0] = o0;

@@ -18,10 +18,13 @@
 //     flagged, four warp-rows of ten would hold one) but appended, one (pixel, channel) per entry, to a per-warp list; whenever 32
 //     entries are waiting the warp replays them side by side, reading the window from global memory (L2 hits: the rows were read
 //     moments ago) as integer bit patterns against weights * 2^100;
-//   * constant channels: the warp tracks, per channel, for how many consecutive rows all 32 + K - 1 pixels of its band were one
-//     value (one XOR pair, one warp reduction, a few byte-parallel operations per row).  K such rows make every window of the band
-//     constant: those channels take flat[value] (the reference's own sequence for a constant window, host-evaluated) and leave the
-//     guard-band test -- alpha = 255 of every real RGBA frame, black sky, clipped highlights.
+//   * constant windows: per staged pixel and channel the kernel counts the consecutive rows in which the pixel equalled its right
+//     neighbour and the pixel above (byte-parallel counters, two staged pixels per lane); eight ballots and a funnel shift per lane
+//     turn them into "all K columns of my window have K such rows", i.e. the window is constant: those channels take flat[value] (the
+//     reference's own sequence for a constant window, host-evaluated) and leave the guard-band test -- alpha = 255 of every real RGBA
+//     frame, black sky, clipped highlights, and the dark plateaus of a decoded JPEG (the reference's Artemis_* images), which a
+//     per-band tracker missed: 604 us instead of 121 us on Artemis_large1024, because every plateau pixel went through the replay in
+//     the few warps that own those bands.
 //
 // Included by rip_blur_sep.cu inside its anonymous namespace, after rip_blur_stream.cuh (bs_* helpers, StreamGeo).
 
@@ -105,13 +108,6 @@ __device__ __noinline__ uint32_t sk_cold(const SepParams &p, const float *rw, in
     return cnt;
 }
 
-// exact bytes of the four channels of a constant window of value word `ref` (rarely needed: when a channel's run reaches K rows)
-__device__ __forceinline__ uint32_t sk_cex(const SepParams &p, uint32_t ref)
-{
-    return (uint32_t)p.flat[ref & 0xffu] | ((uint32_t)p.flat[(ref >> 8) & 0xffu] << 8) | ((uint32_t)p.flat[(ref >> 16) & 0xffu] << 16) |
-           ((uint32_t)p.flat[ref >> 24] << 24);
-}
-
 template <int K>
 __global__ void __launch_bounds__(kSkWarps * 32, K <= 9 ? 5 : 4)
 blur_streamk_kernel(const __grid_constant__ SepParams p, const __grid_constant__ Weights rws, const StreamGeo sg)
@@ -120,7 +116,9 @@ blur_streamk_kernel(const __grid_constant__ SepParams p, const __grid_constant__
     __shared__ __align__(16) uint32_t stage_s[kSkWarps][64 * 4];       // the converted row: 16 bytes (two pairs) per pixel; SW are used, lanes >= 2 HALF park their B pixel behind
     __shared__ uint32_t list_s[kSkWarps][kSkList];
     __shared__ float rw_s[K * K];   // the reference's weights * 2^100 for the replay (a generic load from the parameter bank per tap was its critical path)
+    __shared__ __align__(4) uint8_t flat_s[256];   // flat[v] (a lookup by pixel value: per-lane addresses, which the constant bank serialises)
     for (int i = threadIdx.x; i < K * K; i += kSkWarps * 32) rw_s[i] = rws.w[i];
+    for (int i = threadIdx.x; i < 64; i += kSkWarps * 32) reinterpret_cast<uint32_t *>(flat_s)[i] = reinterpret_cast<const uint32_t *>(p.flat)[i];
     __syncthreads();   // (the only block-level barrier: before any warp leaves)
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -166,10 +164,14 @@ blur_streamk_kernel(const __grid_constant__ SepParams p, const __grid_constant__
     for (int k = 0; k < K - 1; k++) acc[k][0] = acc[k][1] = 0ull;
     const bs_u64 BIAS = bs_pk2(p.sbias, p.sbias);
 
-    // the band's constant-channel tracker (all warp-uniform): the value word of the row above, and per channel (one byte each) the
-    // number of consecutive rows, ending at the current one, in which all SW pixels were that value; saturates at 128
-    uint32_t prevref = 0, run = 0, cnt = 0, cm = 0, cex = 0;   // cm: 0xff per channel with >= K constant rows behind it; cex: their exact bytes
-
+    // The constant-window tracker, per staged pixel and channel (one byte each): the number of consecutive rows, ending at the current
+    // one, in which the pixel equalled its right neighbour and the pixel above it; saturates at 127.  K such rows in each of the K
+    // columns of a window make the window constant.  (Until the end of round 2 the tracker was per BAND -- all 32 + K - 1 pixels of a row
+    // one value: fine for alpha and for regions wider than the band, but the dark plateaus of a decoded JPEG are narrower.  On the
+    // reference's Artemis_large1024 image, 5 % of whose 17x17 windows are constant and not black, every such pixel went through the
+    // 289-tap replay, all in the few warps that own those bands: 604 us against 86 us for the tiled kernel.)
+    uint32_t pva = na, pvb = nb, runA = 0, runB = 0, cnt = 0;
+    uint32_t cexsrc = ~na, cex = 0;   // the pixel word the exact bytes `cex` were last looked up for
     const int r_last = ye - 1 + HALF;
 #pragma unroll 1
     for (int r = ys - HALF; r <= r_last; r++) {
@@ -183,17 +185,27 @@ blur_streamk_kernel(const __grid_constant__ SepParams p, const __grid_constant__
         }
         ma = __ldg(pa);
         mb = __ldg(pb);
-        // tracker
+        // tracker: which channels of this lane's window (staged columns lane .. lane + K - 1, rows r - K + 1 .. r) are constant
+        uint32_t cm = 0;   // 0xff per constant channel
         {
-            const uint32_t ref = __shfl_sync(0xffffffffu, qa, 0);
-            const uint32_t t = __reduce_or_sync(0xffffffffu, (qa ^ ref) | (qb ^ ref)) | (ref ^ prevref);
-            prevref = ref;
-            run += 0x01010101u;
-            run -= (run >> 7) & 0x01010101u;
-            run &= ~bs_nzb(t);
-            const uint32_t cm_new = bs_nzb((run + (uint32_t)(128 - K) * 0x01010101u) & 0x80808080u);
-            if (cm_new & ~cm) cex = sk_cex(p, ref);   // warp-uniform, rare: a channel's run just reached K rows
-            cm = cm_new;
+            const uint32_t ra = __shfl_down_sync(0xffffffffu, qa, 1), rb0 = __shfl_sync(0xffffffffu, qb, 0), rbn = __shfl_down_sync(0xffffffffu, qb, 1);
+            const uint32_t right_a = lane == 31u ? rb0 : ra;   // staged column 32 is lane 0's B pixel
+            const uint32_t ea = (qa ^ right_a) | (qa ^ pva), eb = (qb ^ rbn) | (qb ^ pvb);   // (B pixels of lanes >= 2 HALF - 1 are never looked at)
+            pva = qa;
+            pvb = qb;
+            runA += 0x01010101u;
+            runA -= (runA >> 7) & 0x01010101u;
+            runA &= ~bs_nzb(ea);
+            runB += 0x01010101u;
+            runB -= (runB >> 7) & 0x01010101u;
+            runB &= ~bs_nzb(eb);
+            const uint32_t ga = runA + (uint32_t)(128 - K) * 0x01010101u, gb = runB + (uint32_t)(128 - K) * 0x01010101u;   // bit 7 of a byte: K good rows
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t A = __ballot_sync(0xffffffffu, (ga >> (8 * c + 7)) & 1u), B = __ballot_sync(0xffffffffu, (gb >> (8 * c + 7)) & 1u);
+                const uint32_t w = __funnelshift_r(A, B, lane);   // bit k: staged column lane + k
+                if ((~w & ((1u << K) - 1u)) == 0u) cm |= 0xffu << (8 * c);
+            }
         }
         // stage the converted pixels (integer bit patterns: q * 2^-149; the taps carry the powers of two back)
         const uint32_t sb = st;
@@ -241,7 +253,12 @@ blur_streamk_kernel(const __grid_constant__ SepParams p, const __grid_constant__
             uint32_t z0 = bs_lo(f0) << (32 - kSepFracBits), z1 = bs_hi(f0) << (32 - kSepFracBits), z2 = bs_lo(f1) << (32 - kSepFracBits),
                      z3 = bs_hi(f1) << (32 - kSepFracBits);
             uint32_t o = bs_pack(f0, f1);
-            if (cm) {   // warp-uniform: channels with K constant rows behind them take the table's value and leave the guard-band test
+            if (cm) {   // constant channels take the table's value (any pixel of the window gives it: this lane's A pixel is its first column) and leave the guard-band test
+                if ((qa ^ cexsrc) & cm) {   // (alpha = 255 frames: looked up once)
+                    cexsrc = qa;
+                    cex = (uint32_t)flat_s[qa & 0xffu] | ((uint32_t)flat_s[(qa >> 8) & 0xffu] << 8) | ((uint32_t)flat_s[(qa >> 16) & 0xffu] << 16) |
+                          ((uint32_t)flat_s[qa >> 24] << 24);
+                }
                 o = (o & ~cm) | (cex & cm);
                 z0 |= bs_rep<0>(cm);
                 z1 |= bs_rep<1>(cm);
@@ -250,7 +267,8 @@ blur_streamk_kernel(const __grid_constant__ SepParams p, const __grid_constant__
             }
             if (store) *po = o;   // (before the cold block: a replay below may patch bytes of this very row)
             po += p.W;
-            const bool flag = min(__vimin3_u32(z0, z1, z2), z3) < p.zthr && store;
+            // (a channel whose fast value is 0 needs no fix: black regions -- colour bytes all 0, alpha out of the band -- do not even visit the cold block)
+            const bool flag = min(__vimin3_u32(z0, z1, z2), z3) < p.zthr && store && !((o & 0x00ffffffu) == 0u && z3 >= p.zthr);
             if (__any_sync(0xffffffffu, flag)) {
                 uint32_t fm = 0;   // flagged channels whose fast value is not 0
                 if (flag)

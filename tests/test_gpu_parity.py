@@ -251,6 +251,27 @@ def test_blur_streaming_k_kernel_1080p_default(ctx, oracle):
         _eq(got[i], oracle.blur(imgs[i], 17, weights=w, threads=0), f"17x17 1080p frame {i}")
 
 
+@pytest.mark.parametrize("k,sigma,stream", [(5, 1.0, 0), (5, 1.0, 1), (5, 1.5, 1), (9, 2.5, 1), (17, 6.0, 0), (17, 6.0, 1)])
+def test_blur_black_sky_with_stars(ctx, oracle, k, sigma, stream, opt):
+    """The reference's Artemis_* images: black sky that is not quite constant (a few dim pixels, a few stars), alpha = 255.  A channel whose
+    fast value is 0 needs no replay (its true sum is >= 0 and below 1) -- but sums just below 1, 2, ... still do."""
+    opt("RIP_BLUR_STREAM" if stream else "RIP_BLUR_TILED", 1)
+    h, wd = 150, 260
+    rng = np.random.default_rng(404)
+    img = np.zeros((h, wd, 4), np.uint8)
+    img[..., 3] = 255
+    dim = rng.random((h, wd)) < 0.02
+    img[dim, :3] = rng.integers(1, 4, (int(dim.sum()), 3), dtype=np.uint8)
+    stars = rng.random((h, wd)) < 0.002
+    img[stars, :3] = rng.integers(100, 256, (int(stars.sum()), 3), dtype=np.uint8)
+    img[100:, 180:, :3] = rng.integers(0, 256, (50, 80, 3), dtype=np.uint8)   # the lit limb
+    img[60:90, 40:120, 2] = 1                                                 # a faint flat glow: blurred sums sit on / just below 1
+    w = rip.gauss_weights(k, sigma)
+    _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), oracle.blur(img, k, weights=w, threads=0), f"black sky K={k} stream={stream}")
+    g = np.ascontiguousarray(img[..., 2])
+    _eq(ctx.process(g, rip.OP_GAUSSIAN, rip.FMT_GRAY8, ksize=k, weights=w), oracle.blur(g, k, weights=w, threads=0), f"black sky, gray K={k}")
+
+
 def test_blur_rejects_bad_arguments(ctx):
     img = np.zeros((8, 8, 4), np.uint8)
     with pytest.raises(rip.RipError):
