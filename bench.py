@@ -63,6 +63,14 @@ def content_frame(kind: str, h: int = H, w: int = W) -> np.ndarray:
         yy, xx = np.mgrid[0:h, 0:w]
         sm = (128 + 60 * np.sin(xx / 97.0) + 50 * np.cos(yy / 61.0) + rng.integers(-2, 3, (h, w))).clip(0, 255).astype(np.uint8)
         return np.ascontiguousarray(np.stack([sm, np.roll(sm, 7, 1), np.roll(sm, 13, 0)], -1))
+    if kind in ("artemis_tiled", "tulips_tiled"):   # the reference's own images (decoded pixels from tests/golden), tiled to the frame size
+        name = "Artemis_large1024.bgr" if kind == "artemis_tiled" else "Tulips_medium640.bgr"
+        try:
+            rgb = np.ascontiguousarray(dict(np.load(os.path.join(ROOT, "tests", "golden", "images.npz")))[name][..., ::-1])
+        except Exception:
+            return None
+        reps = (-(-h // rgb.shape[0]), -(-w // rgb.shape[1]), 1)
+        return np.ascontiguousarray(np.tile(rgb, reps)[:h, :w])
     one = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
     if kind == "letterbox25":  # 25 % of the rows are black bars
         one[: h // 8] = 0
@@ -232,8 +240,10 @@ def gpu_median_us(rip, fn, dev: int, stream, n: int = 7, warm: int = 2) -> float
 
 def content_rows(rip, dev, stream, d_in, d_out, weights, peak, n=FRAMES_PER_GPU) -> list:
     rows = []
-    for kind in ("smooth", "letterbox25", "half_clipped", "flat", "black"):
+    for kind in ("smooth", "artemis_tiled", "tulips_tiled", "letterbox25", "half_clipped", "flat", "black"):
         one = content_frame(kind)
+        if one is None:
+            continue
         for i in range(n):   # n shifted copies: every frame differs, constant regions stay constant
             d_in.upload(np.roll(one, 17 * i, axis=1), offset=i * one.nbytes)
         fn = lambda: rip.fused_dev(d_in.ptr, d_out.ptr, W, H, n, rip.FMT_RGB8, KSIZE, weights, device=dev, stream=stream)  # noqa: E731

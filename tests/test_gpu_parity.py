@@ -491,6 +491,32 @@ def test_fused_flat_regions_are_exact(ctx, oracle, sigma):
     _eq(ctx.process(g, rip.OP_FUSED, rip.FMT_GRAY8, ksize=5, weights=w), oracle.sobel(oracle.blur(g, 5, weights=w, threads=0)), "flat regions, gray input")
 
 
+@pytest.mark.parametrize("sigma", [1.0, 1.5])
+@pytest.mark.parametrize("npx", [8, 4])
+def test_fused_plateaus_of_real_images(ctx, oracle, golden_images, sigma, npx, opt):
+    """Decoded JPEGs (the reference's own images): dark plateaus a few pixels wide, where several pixels of a lane sit inside the guard
+    band with constant 5x5 windows while the lane's neighbourhood as a whole is not constant -- the per-pixel constant-window pass of the
+    cold path.  Also synthetic patches of every small size next to each other, and patches that differ by one level."""
+    opt("RIP_FUSED_NPX", npx)
+    w = rip.gauss_weights(5, sigma)
+    for name in ("Artemis_large1024", "Tulips_medium640"):
+        bgr = golden_images[name + ".bgr"]
+        rgb = np.ascontiguousarray(bgr[:, : bgr.shape[1] // 8 * 8, ::-1])
+        _eq(ctx.process(rgb, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(rgb, 5, weights=w, threads=0), f"{name} sigma {sigma} npx {npx}")
+    rng = np.random.default_rng(606)
+    h, wd = 160, 512
+    img = rng.integers(0, 256, (h, wd, 3), dtype=np.uint8)
+    for i in range(60):   # plateaus of 3..14 pixels, grey (r = g = b: the gray stage's own cold path too) and coloured
+        y, x, sy, sx = rng.integers(0, h - 16), rng.integers(0, wd - 16), rng.integers(3, 15), rng.integers(3, 15)
+        v = int(rng.integers(1, 256))
+        img[y: y + sy, x: x + sx] = (v, v, v) if i % 2 else tuple(int(t) for t in rng.integers(0, 256, 3))
+    img[100:130, 200:300] = 7
+    img[110:120, 230:260] = 8             # one level up inside a plateau
+    gray_in = np.ascontiguousarray(img[..., 0])
+    _eq(ctx.process(img, rip.OP_FUSED, rip.FMT_RGB8, ksize=5, weights=w), oracle.fused(img, 5, weights=w, threads=0), f"patches sigma {sigma} npx {npx}")
+    _eq(ctx.process(gray_in, rip.OP_FUSED, rip.FMT_GRAY8, ksize=5, weights=w), oracle.sobel(oracle.blur(gray_in, 5, weights=w, threads=0)), "patches, gray input")
+
+
 def test_fused_guard_band_statistics():
     """The exact replay must actually trigger (flat frames: always) yet stay rare on noise."""
     w = rip.gauss_weights(5, 1.0)

@@ -45,6 +45,10 @@ elif a.kind == "halfflat77":  # half of the frame is a constant mid-grey region
 elif a.kind == "halfflat_odd":  # the constant region ends inside a lane
     one = rng.integers(0, 256, (a.h, a.w, 3), dtype=np.uint8)
     one[:, : a.w // 2 + 13] = 255
+elif a.kind in ("artemis", "tulips"):   # the reference's own images (decoded pixels from tests/golden), tiled to the frame size
+    name = "Artemis_large1024.bgr" if a.kind == "artemis" else "Tulips_medium640.bgr"
+    rgb = np.ascontiguousarray(dict(np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "images.npz")))[name][..., ::-1])
+    one = np.ascontiguousarray(np.tile(rgb, (-(-a.h // rgb.shape[0]), -(-a.w // rgb.shape[1]), 1))[: a.h, : a.w])
 elif a.kind == "flat255":
     one = np.full((a.h, a.w, 3), 255, np.uint8)
 else:
