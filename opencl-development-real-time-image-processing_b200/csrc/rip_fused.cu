@@ -35,7 +35,7 @@
 #define RIP_X2_MINB8 4
 #endif
 #ifndef RIP_X2_MINB8_NOBLUR
-#define RIP_X2_MINB8_NOBLUR 5   // colour -> gray -> Sobel: five blocks (20 warps) per SM (config 3: 127 -> 123 us; gray input is better off with 4)
+#define RIP_X2_MINB8_NOBLUR 6   // colour -> gray -> Sobel: six blocks (24 warps) per SM since the row buffers left the registers (76 registers; config 3: 121 -> 117 us; five before: 127 -> 123 us; gray input is better off with 4)
 #endif
 #ifndef RIP_X2_MINB4
 #define RIP_X2_MINB4 6

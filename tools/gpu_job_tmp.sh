@@ -1,4 +1,9 @@
 #!/bin/bash
-timeout 600 python -m pytest tests -m gpu -x -q -k "blur or gauss" 2>&1 | tail -n 3
-python tools/prof_blur_artemis.py
-python tools/prof_blur_small.py | grep "17x17\|9x9"
+for rep in 1 2; do
+for lib in default tools/ab/nb7.so; do
+  echo "== $lib"
+  if [ $lib != default ]; then export RIP_LIB_PATH=$PWD/$lib; else unset RIP_LIB_PATH; fi
+  python tools/prof_fused.py --op sobel --frames 64 --w 1920 --h 1080 --launches 10
+  python tools/prof_fused.py --op sobel --frames 32 --launches 10
+done
+done
