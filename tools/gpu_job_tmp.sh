@@ -1,9 +1,11 @@
 #!/bin/bash
 for rep in 1 2; do
-for lib in default tools/ab/nb7.so; do
-  echo "== $lib"
+for seg in 0 128 240; do
+for lib in default tools/ab/minb5c.so; do
+  echo "== $lib seg $seg"
   if [ $lib != default ]; then export RIP_LIB_PATH=$PWD/$lib; else unset RIP_LIB_PATH; fi
-  python tools/prof_fused.py --op sobel --frames 64 --w 1920 --h 1080 --launches 10
-  python tools/prof_fused.py --op sobel --frames 32 --launches 10
+  if [ $seg != 0 ]; then export RIP_FUSED_SEG=$seg; else unset RIP_FUSED_SEG; fi
+  python tools/prof_fused.py --frames 32 --launches 8
+done
 done
 done
