@@ -384,6 +384,36 @@ static void plan_stream_alpha(SepParams &p)
     memcpy(&p.f255, &f255, 4);
 }
 
+// the same proof for the streaming KxK kernel, whose chains run the other way round: horizontal from g[0] (sg1), vertical on the bias (sg2)
+static void plan_streamk_alpha(SepParams &p, int K)
+{
+    auto den = [](uint32_t q) { float f; memcpy(&f, &q, 4); return f; };   // q * 2^-149
+    auto hsum = [&](int k_low) {   // the row sum with pixel k_low one step below 255 (k_low < 0: all 255)
+        volatile float a = p.sg1[0] * den(k_low == 0 ? 254u : 255u);
+        for (int k = 1; k < K; k++) a = std::fmaf(p.sg1[k], den(k_low == k ? 254u : 255u), a);
+        return (float)a;
+    };
+    p.f255 = 0;
+    p.a255 = (uint32_t)p.flat[255] << 24;
+    const float h255 = hsum(-1);
+    float hsec = 0.0f;   // the largest row sum of a row that is not all 255
+    for (int k = 0; k < K; k++) {
+        const float h = hsum(k);
+        if (!(h < h255)) return;
+        hsec = h > hsec ? h : hsec;
+    }
+    auto vsum = [&](int k_low) {
+        volatile float a = p.sbias;
+        for (int k = 0; k < K; k++) a = std::fmaf(p.sg2[k], k_low == k ? hsec : h255, a);
+        return (float)a;
+    };
+    const float f255 = vsum(-1);
+    for (int k = 0; k < K; k++)
+        if (!(vsum(k) < f255)) return;
+    if (!(f255 >= 256.0f && f255 < 512.0f)) return;
+    memcpy(&p.f255, &f255, 4);
+}
+
 template <int CN>
 static int launch_sep_cn(cudaStream_t s, const SepParams &p, const Weights &wts, dim3 grid, size_t smem)
 {
@@ -467,6 +497,8 @@ int launch_blur_sep(cudaStream_t s, const uint8_t *src, uint8_t *dst, int W, int
                     }
                     memcpy(q.rw, plan.rws.w, sizeof(q.rw));
                     plan_stream_alpha(q);
+                } else if (plan.streamk_ok) {
+                    plan_streamk_alpha(q, ksize);
                 }
             }
         }

@@ -186,8 +186,7 @@ blur_streamk_kernel(const __grid_constant__ SepParams p, const __grid_constant__
         ma = __ldg(pa);
         mb = __ldg(pb);
         // tracker: which channels of this lane's window (staged columns lane .. lane + K - 1, rows r - K + 1 .. r) are constant
-        uint32_t cm = 0;   // 0xff per constant channel
-        {
+        {   // (the counters run every row; the window test -- eight ballots -- only when some lane has a channel inside the band, below)
             const uint32_t ra = __shfl_down_sync(0xffffffffu, qa, 1), rb0 = __shfl_sync(0xffffffffu, qb, 0), rbn = __shfl_down_sync(0xffffffffu, qb, 1);
             const uint32_t right_a = lane == 31u ? rb0 : ra;   // staged column 32 is lane 0's B pixel
             const uint32_t ea = (qa ^ right_a) | (qa ^ pva), eb = (qb ^ rbn) | (qb ^ pvb);   // (B pixels of lanes >= 2 HALF - 1 are never looked at)
@@ -199,13 +198,6 @@ blur_streamk_kernel(const __grid_constant__ SepParams p, const __grid_constant__
             runB += 0x01010101u;
             runB -= (runB >> 7) & 0x01010101u;
             runB &= ~bs_nzb(eb);
-            const uint32_t ga = runA + (uint32_t)(128 - K) * 0x01010101u, gb = runB + (uint32_t)(128 - K) * 0x01010101u;   // bit 7 of a byte: K good rows
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const uint32_t A = __ballot_sync(0xffffffffu, (ga >> (8 * c + 7)) & 1u), B = __ballot_sync(0xffffffffu, (gb >> (8 * c + 7)) & 1u);
-                const uint32_t w = __funnelshift_r(A, B, lane);   // bit k: staged column lane + k
-                if ((~w & ((1u << K) - 1u)) == 0u) cm |= 0xffu << (8 * c);
-            }
         }
         // stage the converted pixels (integer bit patterns: q * 2^-149; the taps carry the powers of two back)
         const uint32_t sb = st;
@@ -253,23 +245,41 @@ blur_streamk_kernel(const __grid_constant__ SepParams p, const __grid_constant__
             uint32_t z0 = bs_lo(f0) << (32 - kSepFracBits), z1 = bs_hi(f0) << (32 - kSepFracBits), z2 = bs_lo(f1) << (32 - kSepFracBits),
                      z3 = bs_hi(f1) << (32 - kSepFracBits);
             uint32_t o = bs_pack(f0, f1);
-            if (cm) {   // constant channels take the table's value (any pixel of the window gives it: this lane's A pixel is its first column) and leave the guard-band test
-                if ((qa ^ cexsrc) & cm) {   // (alpha = 255 frames: looked up once)
-                    cexsrc = qa;
-                    cex = (uint32_t)flat_s[qa & 0xffu] | ((uint32_t)flat_s[(qa >> 8) & 0xffu] << 8) | ((uint32_t)flat_s[(qa >> 16) & 0xffu] << 16) |
-                          ((uint32_t)flat_s[qa >> 24] << 24);
+            // alpha: a fast sum equal to that of an all-255 window proves the window IS all 255 (plan_streamk_alpha, the argument of the 5x5
+            // kernel): exact value from the table, out of the guard-band test -- the alpha channel of every frame the reference uploads
+            if (bs_hi(f1) == p.f255) {
+                z3 = 0xffffffffu;
+                o = (o & 0x00ffffffu) | p.a255;
+            }
+            // (a channel whose fast value is 0 needs no fix: black regions -- colour bytes all 0, alpha out of the band -- do not get any further)
+            bool flag = min(__vimin3_u32(z0, z1, z2), z3) < p.zthr && store && !((o & 0x00ffffffu) == 0u && z3 >= p.zthr);
+            const bool any = __any_sync(0xffffffffu, flag);
+            if (any) {   // warp-uniform: which channels of this lane's window (staged columns lane .. lane + K - 1, rows r - K + 1 .. r) are constant?
+                uint32_t cm = 0;   // 0xff per constant channel
+                const uint32_t ga = runA + (uint32_t)(128 - K) * 0x01010101u, gb = runB + (uint32_t)(128 - K) * 0x01010101u;   // bit 7 of a byte: K good rows
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint32_t A = __ballot_sync(0xffffffffu, (ga >> (8 * c + 7)) & 1u), B = __ballot_sync(0xffffffffu, (gb >> (8 * c + 7)) & 1u);
+                    const uint32_t w = __funnelshift_r(A, B, lane);   // bit k: staged column lane + k
+                    if ((~w & ((1u << K) - 1u)) == 0u) cm |= 0xffu << (8 * c);
                 }
-                o = (o & ~cm) | (cex & cm);
-                z0 |= bs_rep<0>(cm);
-                z1 |= bs_rep<1>(cm);
-                z2 |= bs_rep<2>(cm);
-                z3 |= bs_rep<3>(cm);
+                if (cm) {   // constant channels take the table's value (any pixel of the window gives it: this lane's A pixel is its first column) and leave the test
+                    if ((qa ^ cexsrc) & cm) {
+                        cexsrc = qa;
+                        cex = (uint32_t)flat_s[qa & 0xffu] | ((uint32_t)flat_s[(qa >> 8) & 0xffu] << 8) | ((uint32_t)flat_s[(qa >> 16) & 0xffu] << 16) |
+                              ((uint32_t)flat_s[qa >> 24] << 24);
+                    }
+                    o = (o & ~cm) | (cex & cm);
+                    z0 |= bs_rep<0>(cm);
+                    z1 |= bs_rep<1>(cm);
+                    z2 |= bs_rep<2>(cm);
+                    z3 |= bs_rep<3>(cm);
+                    flag = min(__vimin3_u32(z0, z1, z2), z3) < p.zthr && store && !((o & 0x00ffffffu) == 0u && z3 >= p.zthr);
+                }
             }
             if (store) *po = o;   // (before the cold block: a replay below may patch bytes of this very row)
             po += p.W;
-            // (a channel whose fast value is 0 needs no fix: black regions -- colour bytes all 0, alpha out of the band -- do not even visit the cold block)
-            const bool flag = min(__vimin3_u32(z0, z1, z2), z3) < p.zthr && store && !((o & 0x00ffffffu) == 0u && z3 >= p.zthr);
-            if (__any_sync(0xffffffffu, flag)) {
+            if (any && __any_sync(0xffffffffu, flag)) {
                 uint32_t fm = 0;   // flagged channels whose fast value is not 0
                 if (flag)
                     fm = (z0 < p.zthr && (o & 0xffu) ? 1u : 0u) | (z1 < p.zthr && (o & 0xff00u) ? 2u : 0u) | (z2 < p.zthr && (o & 0xff0000u) ? 4u : 0u) |

@@ -205,6 +205,21 @@ def test_blur_constant_channels_take_the_table(ctx, oracle, k, sigma, stream, op
     _eq(ctx.process(g, rip.OP_GAUSSIAN, rip.FMT_GRAY8, ksize=k, weights=w), oracle.blur(g, k, weights=w, threads=0), f"constant regions, gray K={k}")
 
 
+@pytest.mark.parametrize("k,sigma", [(9, 2.5), (17, 6.0), (17, 2.0)])
+def test_blur_streaming_k_alpha_255_shortcut_is_exact(ctx, oracle, k, sigma, opt):
+    """The same shortcut in the streaming KxK kernel (its chains run horizontal-first): near misses must not take it."""
+    opt("RIP_BLUR_STREAM", 1)
+    h, wd = 90, 200
+    rng = np.random.default_rng(78)
+    img = rng.integers(0, 256, (h, wd, 4), dtype=np.uint8)
+    img[..., 3] = 255
+    img[5::23, 7::31, 3] = 254
+    img[40:70, 100:180, 3] = rng.integers(253, 256, (30, 80), dtype=np.uint8)
+    img[60:, :40, :3] = 255
+    w = rip.gauss_weights(k, sigma)
+    _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), oracle.blur(img, k, weights=w, threads=0), f"alpha shortcut K={k} sigma {sigma}")
+
+
 @pytest.mark.parametrize("sigma", [1.0, 1.5, 0.6])
 def test_blur_streaming_alpha_255_shortcut_is_exact(ctx, oracle, sigma, opt):
     """The streaming kernel takes alpha from the constant-window table when the fast sum equals that of an all-255 window (proved on
