@@ -220,6 +220,21 @@ def test_blur_streaming_k_alpha_255_shortcut_is_exact(ctx, oracle, k, sigma, opt
     _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), oracle.blur(img, k, weights=w, threads=0), f"alpha shortcut K={k} sigma {sigma}")
 
 
+@pytest.mark.parametrize("k,sigma", [(9, 2.5), (17, 6.0)])
+def test_blur_streaming_k_constant_value_is_the_complement_of_the_first_row(ctx, oracle, k, sigma, opt):
+    """Regression (found by tools/soak.py): the cached table bytes of the constant-window shortcut were keyed on a sentinel ~(first row), so a
+    channel that is 0 in the segment's first row and constant 255 further down took a stale 0."""
+    opt("RIP_BLUR_STREAM", 1)
+    h, wd = 120, 200
+    rng = np.random.default_rng(79)
+    img = rng.integers(0, 256, (h, wd, 4), dtype=np.uint8)   # (alpha is noise: nothing else refreshes the cache)
+    img[:10, :, :3] = 0
+    img[40:100, 30:150, :3] = 255
+    img[50:90, 160:, 1] = 0
+    w = rip.gauss_weights(k, sigma)
+    _eq(ctx.process(img, rip.OP_GAUSSIAN, rip.FMT_RGBA8, ksize=k, weights=w), oracle.blur(img, k, weights=w, threads=0), f"complement K={k}")
+
+
 @pytest.mark.parametrize("sigma", [1.0, 1.5, 0.6])
 def test_blur_streaming_alpha_255_shortcut_is_exact(ctx, oracle, sigma, opt):
     """The streaming kernel takes alpha from the constant-window table when the fast sum equals that of an all-255 window (proved on
