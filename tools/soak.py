@@ -20,6 +20,7 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rng = np.random.default_rng(seed)
 ctx = rip.Context([0])
+BIG = int(os.environ.get("SOAK_BIG", "1"))   # scale of the random shapes (1: up to 260 x 400; 5: up to 1300 x 2000 -- several segments and band groups)
 
 
 def content(h, w, c):
@@ -62,7 +63,7 @@ while time.time() - t0 < budget:
         k = int(rng.choice([5, 5, 9, 17, 3, 7]))
         sigma = float(rng.choice([0.6, 1.0, 1.5, 2.5, 4.0, 6.0]))
         nf = int(rng.integers(1, 4))
-        h, w = int(rng.integers(k, 260)), int(rng.integers(k, 400))
+        h, w = int(rng.integers(k, 260 * BIG)), int(rng.integers(k, 400 * BIG))
         force = rng.choice(["", "RIP_BLUR_STREAM", "RIP_BLUR_TILED"])
         if force:
             rip.set_option(force, 1)
@@ -79,7 +80,7 @@ while time.time() - t0 < budget:
     else:
         fmt, c = [(rip.FMT_RGB8, 3), (rip.FMT_RGBA8, 4), (rip.FMT_GRAY8, 1), (rip.FMT_BGR8, 3)][int(rng.integers(0, 4))]
         nf = int(rng.integers(1, 3))
-        h, w = int(rng.integers(8, 300)), int(rng.integers(2, 80)) * int(rng.choice([4, 8, 8]))
+        h, w = int(rng.integers(8, 300 * BIG)), int(rng.integers(2, 80 * BIG)) * int(rng.choice([4, 8, 8]))
         sigma = float(rng.choice([1.0, 1.5]))
         imgs = np.stack([content(h, w, c) for _ in range(nf)])
         if c == 1:
