@@ -172,7 +172,7 @@ blur_streamk_kernel(const __grid_constant__ SepParams p, const __grid_constant__
     // 289-tap replay, all in the few warps that own those bands: 604 us against 86 us for the tiled kernel.)
     uint32_t pva = na, pvb = nb, runA = 0, runB = 0, cnt = 0;
     // the pixel word the exact bytes `cex` were last looked up for (valid from the start: a sentinel such as ~na collides with a channel whose value
-    // is the complement of the first row's -- 0 then 255 -- and leaves 0 in the output: found by tools/soak.py)
+    // is the complement of the first row's -- 0 then 255 -- and leaves 0 in the output: found by tests/soak.py)
     uint32_t cexsrc = na, cex = (uint32_t)flat_s[na & 0xffu] | ((uint32_t)flat_s[(na >> 8) & 0xffu] << 8) | ((uint32_t)flat_s[(na >> 16) & 0xffu] << 16) |
                                 ((uint32_t)flat_s[na >> 24] << 24);
     const int r_last = ye - 1 + HALF;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Randomised parity soak of the CUDA kernels against the oracle (not part of the test suite: run once per build on a GPU box).
+"""Randomised parity soak of the CUDA kernels against the oracle (test infrastructure; not collected by pytest: run once per build on a GPU box).
 
-    python tools/soak.py [seconds=60] [seed=1]
+    python tests/soak.py [seconds=60] [seed=1]
 
 Random kernel sizes, sigmas, shapes (narrow, ragged, batches), formats and content (noise, plateaus of every small size, constant
 channels, black, near-constant alpha), the streaming kernels forced or chosen by size; every output must equal the oracle's bit for bit."""

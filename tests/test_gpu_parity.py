@@ -222,7 +222,7 @@ def test_blur_streaming_k_alpha_255_shortcut_is_exact(ctx, oracle, k, sigma, opt
 
 @pytest.mark.parametrize("k,sigma", [(9, 2.5), (17, 6.0)])
 def test_blur_streaming_k_constant_value_is_the_complement_of_the_first_row(ctx, oracle, k, sigma, opt):
-    """Regression (found by tools/soak.py): the cached table bytes of the constant-window shortcut were keyed on a sentinel ~(first row), so a
+    """Regression (found by tests/soak.py): the cached table bytes of the constant-window shortcut were keyed on a sentinel ~(first row), so a
     channel that is 0 in the segment's first row and constant 255 further down took a stale 0."""
     opt("RIP_BLUR_STREAM", 1)
     h, wd = 120, 200
