@@ -302,6 +302,47 @@ def test_blur_black_sky_with_stars(ctx, oracle, k, sigma, stream, opt):
     _eq(ctx.process(g, rip.OP_GAUSSIAN, rip.FMT_GRAY8, ksize=k, weights=w), oracle.blur(g, k, weights=w, threads=0), f"black sky, gray K={k}")
 
 
+@pytest.mark.parametrize("shape", [(2, 131, 248), (1, 75, 76), (3, 40, 1000)])
+def test_device_ops_stay_inside_their_output_buffers(oracle, shape, opt):
+    """compute-sanitizer is closed on this GPU pool, so the bounds check is our own: every device-API operation writes into the middle of
+    a canary-filled buffer (256 KB on either side) -- the canaries must
+    survive and the payload must equal the oracle's.  Covers the byte-granular patch stores of the deferred replays (streaming KxK
+    kernel), the predicated stores of partial bands and the halo lanes of every streaming kernel."""
+    n, h, wd = shape
+    rng = np.random.default_rng(515)
+    pad = 256 * 1024
+    rgba = rng.integers(0, 256, (n, h, wd, 4), dtype=np.uint8)
+    rgba[-1, ..., 3] = 255
+    rgba[-1, : h // 2, : wd // 2, :3] = 0
+    rgba[0, h // 3:, wd // 3:, :3] = 255
+    rgb = np.ascontiguousarray(rgba[..., :3])
+    d_rgba = rip.DeviceBuffer(rgba.nbytes).upload(rgba)
+    d_rgb = rip.DeviceBuffer(rgb.nbytes).upload(rgb)
+
+    def run(name, out_bytes, launch, want):
+        buf = rip.DeviceBuffer(out_bytes + 2 * pad)
+        buf.upload(np.full(out_bytes + 2 * pad, 0xA5, np.uint8))
+        launch(buf.ptr + pad)
+        got = buf.download((out_bytes + 2 * pad,))
+        assert (got[:pad] == 0xA5).all() and (got[pad + out_bytes:] == 0xA5).all(), f"{name} {shape}: wrote outside its output"
+        _eq(got[pad: pad + out_bytes].reshape(want.shape), want, f"{name} {shape}")
+        buf.free()
+
+    for k, sigma in ((5, 1.0), (9, 2.5), (17, 6.0)):
+        w = rip.gauss_weights(k, sigma)
+        want = np.stack([oracle.blur(rgba[i], k, weights=w, threads=0) for i in range(n)])
+        for force in ("RIP_BLUR_STREAM", "RIP_BLUR_TILED"):
+            opt(force, 1)
+            run(f"gauss {k}x{k} {force}", rgba.nbytes, lambda p: rip.gauss_dev(d_rgba.ptr, p, wd, h, n, 4, k, w), want)
+            opt(force, 0)
+    w5 = rip.gauss_weights(5, 1.0)
+    gray = np.stack([oracle.gray(rgb[i], threads=0) for i in range(n)])
+    run("gray", n * h * wd, lambda p: rip.gray_dev(d_rgb.ptr, p, wd, h, n, rip.FMT_RGB8, rip.GRAY_OUT_U8), gray)
+    run("sobel", n * h * wd, lambda p: rip.sobel_dev(d_rgb.ptr, p, wd, h, n, rip.FMT_RGB8), np.stack([oracle.sobel(gray[i]) for i in range(n)]))
+    run("fused", n * h * wd, lambda p: rip.fused_dev(d_rgb.ptr, p, wd, h, n, rip.FMT_RGB8, 5, w5),
+        np.stack([oracle.fused(rgb[i], 5, weights=w5, threads=0) for i in range(n)]))
+
+
 def test_blur_rejects_bad_arguments(ctx):
     img = np.zeros((8, 8, 4), np.uint8)
     with pytest.raises(rip.RipError):
